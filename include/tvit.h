@@ -1,0 +1,194 @@
+/*
+ * tvit.h -- C ABI of libtvit_b200.so: the sm_100a kernels behind the Temporal 3D ViT hot path.
+ *
+ * The reference (anthonylu23/neural-vit) has no native code and no FFI: every op below is reached
+ * there through torch.nn modules in temporal_vit/models/model.py.  Each entry point names the
+ * reference lines whose arithmetic it replaces.  The host side (neural_vit_b200/model.py) mirrors
+ * the reference's Python interface (Temporal3DViTConfig / CONFIGS / Temporal3DViT.forward) and
+ * calls these functions through ctypes with raw device pointers + the current CUDA stream.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are DEVICE pointers owned by the caller (PyTorch's caching
+ *     allocator).  The library never frees or retains them past the stream-ordered call.
+ *   - every function returns TVIT_OK (0) or an error code; tvit_last_error() gives the message.
+ *     Nothing falls back to another implementation silently.
+ *   - all launches go to `stream` (a cudaStream_t).  No host synchronisation inside the library.
+ *   - functions are re-entrant and thread-safe (autograd calls backward from its own thread).
+ *   - "act" tensors use `dtype`: TVIT_F32 (fp32 verification path) or TVIT_BF16 (product path).
+ *     The residual stream, statistics, parameters and parameter gradients are always fp32.
+ *   - matrices are row-major; `ld*` are row strides in ELEMENTS.
+ */
+#ifndef TVIT_H_
+#define TVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tvit_stream_t; /* cudaStream_t */
+
+enum { TVIT_OK = 0, TVIT_ERR_BAD_ARG = 1, TVIT_ERR_CUDA = 2, TVIT_ERR_UNSUPPORTED = 3 };
+enum { TVIT_F32 = 0, TVIT_BF16 = 1 };
+/* SIMT = fp32-accurate CUDA-core kernels (verification path, any dtype);
+ * TCGEN05 = tcgen05/TMEM/TMA tensor-core kernels (bf16 operands, fp32 accumulate). */
+enum { TVIT_ENGINE_SIMT = 0, TVIT_ENGINE_TCGEN05 = 1 };
+
+/* Counter-based dropout descriptor: mask(e) is a pure function of (seed, site, element index e),
+ * so backward regenerates the mask forward used.  p == 0 disables dropout.
+ * Replaces nn.Dropout's ATen Philox stream (model.py:102,104,138,140,224,250). */
+typedef struct {
+  unsigned long long seed;
+  unsigned int site;
+  float p;
+} tvit_dropout;
+
+const char* tvit_last_error(void);
+int tvit_version(void);
+/* 0 iff `device` is compute capability 10.x (B200).  Called before the first forward. */
+int tvit_device_check(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM with fused epilogues: C[M,N] = op(A) * op(B)^T, fp32 accumulate.
+ *   trans_a == 0: A is [M,K] (K contiguous)      trans_a == 1: A is stored [K,M] (M contiguous)
+ *   trans_b == 0: B is [N,K] (K contiguous)      trans_b == 1: B is stored [K,N] (N contiguous)
+ * nn.Linear forward is (trans_a,trans_b) = (0,0) with B = weight; the input-gradient GEMM is (0,0)
+ * with B = weight^T (kept as a bf16 shadow); the weight-gradient GEMM is (1,1) with
+ * A = dY stored [tokens, out] and B = X stored [tokens, in].
+ * Replaces: nn.Linear qkv/proj (model.py:101,103,108,116), fc1/fc2 (:136,139,143,146),
+ * Conv3d patch embed as im2col GEMM (:197-202,300) and their autograd backward (train.py:226).
+ * ------------------------------------------------------------------------------------------- */
+enum {
+  /* out[T][m,n] = acc + bias[n] */
+  TVIT_EPI_STORE = 0,
+  /* h = acc + bias[n]; aux[T][m,n] = h; out[T][m,n] = dropout(gelu_erf(h))        (fc1, :143-145) */
+  TVIT_EPI_BIAS_GELU = 1,
+  /* out_f32[m,n] = resid[m,n] + row_scale[m / rows_per_group] * gamma[n] * dropout(acc + bias[n])
+   * (proj/fc2 + proj_drop/drop2 + LayerScale + DropPath + residual, :116-117,:146-147,:82,:67-71,:176-177) */
+  TVIT_EPI_RESIDUAL = 2,
+  /* out[T][m,n] = acc * dropout_mult(m,n) * gelu'(aux[T][m,n])                  (backward of fc1's GELU/drop1) */
+  TVIT_EPI_GELU_BWD = 3,
+  /* out_f32[m,n] += acc  (atomic; caller zero-fills).  Weight gradients, split along K.  */
+  TVIT_EPI_ACCUM_F32 = 4,
+  /* row m = b * n_patches + i;  out_f32[(b*(n_patches+1) + 1 + i), n] =
+   *   dropout(acc + bias[n] + pos_k[k'][n] + pos_f[f'][n] + pos_t[t'][n])        (:300-313) */
+  TVIT_EPI_PATCH_EMBED = 5
+};
+
+typedef struct {
+  int engine; /* TVIT_ENGINE_* */
+  int dtype;  /* operand (and act output) element type */
+  int trans_a, trans_b;
+  int M, N, K;
+  const void* A;
+  long long lda;
+  const void* B;
+  long long ldb;
+  int epilogue;
+  void* out;
+  long long ldo;
+  const float* bias; /* [N] or NULL */
+  void* aux;         /* BIAS_GELU: pre-activation out; GELU_BWD: pre-activation in */
+  long long ldaux;
+  const float* resid; /* RESIDUAL */
+  long long ldres;
+  const float* gamma;     /* RESIDUAL: [N] or NULL (no LayerScale) */
+  const float* row_scale; /* RESIDUAL: per-sample DropPath multiplier mask/keep, or NULL */
+  int rows_per_group;     /* tokens per sample */
+  tvit_dropout drop;      /* element index = m * N + n (PATCH_EMBED: out_row * N + n) */
+  const float* pos_k;     /* PATCH_EMBED: factorised positional tables */
+  const float* pos_f;
+  const float* pos_t;
+  int Kp, Fp, Tp;
+  int split_k; /* ACCUM_F32: number of K splits, 0 = choose */
+} tvit_gemm_args;
+
+int tvit_gemm(const tvit_gemm_args* args, tvit_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head self-attention over the (trial x frequency x time) token volume, flash style:
+ * no B*H*N*N tensor is materialised; only the per-row log-sum-exp is kept for backward.
+ *   qkv : [B*N, 3*H*hd] act, columns ordered [q(all heads) | k | v], head h = cols h*hd..(h+1)*hd
+ *   out : [B*N, H*hd] act (token-major, heads merged)       lse : [B, H, N] fp32 (natural log)
+ * Dropout on the probabilities: element index = ((b*H + h)*N + q)*N + k.
+ * Replaces model.py:108-115 (reshape/permute, q@k^T*scale, softmax, attn_drop, @v, transpose).
+ * ------------------------------------------------------------------------------------------- */
+int tvit_attn_fwd(int engine, int dtype, const void* qkv, void* out, float* lse, int B, int N, int H, int hd,
+                  const tvit_dropout* drop, tvit_stream_t stream);
+size_t tvit_attn_bwd_workspace_bytes(int engine, int dtype, int B, int N, int H, int hd);
+/* dqkv : [B*N, 3*H*hd] act.  workspace must hold tvit_attn_bwd_workspace_bytes() bytes. */
+int tvit_attn_bwd(int engine, int dtype, const void* qkv, const void* out, const void* dout, const float* lse,
+                  void* dqkv, void* workspace, size_t workspace_bytes, int B, int N, int H, int hd,
+                  const tvit_dropout* drop, tvit_stream_t stream);
+/* probs[b,h,q,k] = softmax(q k^T * hd^-0.5) materialised (interpretability API, model.py:325-350) */
+int tvit_attn_probs(int dtype, const void* qkv, float* probs, int B, int N, int H, int hd, tvit_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bandwidth-bound kernels
+ * ------------------------------------------------------------------------------------------- */
+/* Tubelet im2col + cast: x fp32 (B,K,F,T) -> cols act [B*n, pk*pf*pt], patch order (dk,df,dt),
+ * token order k'*F'*T' + f'*T' + t'.  Replaces the data movement of Conv3d (model.py:197-202,300-303). */
+int tvit_im2col(const float* x, void* cols, int dtype, int B, int K, int F, int T, int pk, int pf, int pt,
+                tvit_stream_t stream);
+
+/* LayerNorm forward over `rows` rows of length D (eps inside sqrt, biased variance): model.py:165,170,244.
+ * x row r starts at x + r * x_row_stride.  y is dense [rows, D].  mean/rstd may be NULL (inference). */
+int tvit_ln_fwd(const float* x, long long x_row_stride, const float* weight, const float* bias, void* y, int dtype,
+                float* mean, float* rstd, long long rows, int D, float eps, tvit_stream_t stream);
+
+/* LayerNorm backward fused with the residual-gradient add and the preparation of the gradient the
+ * preceding residual branch consumes:
+ *   dx[r,:]   = (g_res ? g_res[r,:] : 0) + LN'(dy)[r,:]                      (fp32, row stride dx_row_stride)
+ *   dweight  += sum_r dy * xhat,  dbias += sum_r dy                          (atomic; caller zero-fills)
+ *   if gp:  gp[T][r,:] = dx[r,:] * row_scale[r / rows_per_group] * dropout_mult(r*D + c)
+ *           gp_colsum[c] += sum_r gp (fp32, before rounding)                  (atomic; caller zero-fills)
+ */
+int tvit_ln_bwd(const void* dy, int dtype, const float* x, long long x_row_stride, const float* mean,
+                const float* rstd, const float* weight, const float* g_res, float* dx, long long dx_row_stride,
+                float* dweight, float* dbias, void* gp, const float* row_scale, int rows_per_group,
+                const tvit_dropout* drop, float* gp_colsum, long long rows, int D, tvit_stream_t stream);
+
+/* gp[T][r,c] = g[r,c] * row_scale[r / rows_per_group] * dropout_mult(r*D + c);  colsum[c] += sum_r gp.
+ * Gradient entering a residual branch (backward of DropPath/LayerScale-free part + proj_drop/drop2). */
+int tvit_branch_grad_prep(const float* g, long long rows, int D, const float* row_scale, int rows_per_group,
+                          const tvit_dropout* drop, void* gp, int dtype, float* colsum, tvit_stream_t stream);
+
+/* out[c] += sum_r x[r,c]  (bias gradients).  Caller zero-fills. */
+int tvit_colsum(const void* x, int dtype, long long rows, int C, long long ld, float* out, tvit_stream_t stream);
+
+/* Parameter shadows for the tensor-core path: out[r,c] = w[r,c]; out_t[c,r] = row_scale[r] * w[r,c].
+ * Either output may be NULL; row_scale may be NULL (== 1). */
+int tvit_cast_weight(const float* w, int R, int C, const float* row_scale, void* out, void* out_t, int dtype,
+                     tvit_stream_t stream);
+
+/* Finish the gradients of  z = gamma (.) (a W^T + b)  from  G = gp^T a  and  cs = colsum(gp):
+ *   dW[r,c] = gamma[r] * G[r,c];  dgamma[r] = sum_c W[r,c] G[r,c] + b[r] cs[r];  db[r] = gamma[r] cs[r].
+ * gamma == NULL means no LayerScale (dW = G, db = cs, dgamma untouched).  (model.py:74-82 backward) */
+int tvit_ls_finalize(const float* G, const float* W, const float* gamma, const float* bias, const float* cs,
+                     float* dW, float* dgamma, float* dbias, int R, int C, tvit_stream_t stream);
+
+/* h[b,0,:] = dropout(cls[:])  -- CLS prepend (model.py:309-313); element index = (b*N)*D + c. */
+int tvit_cls_rows(const float* cls, float* h, int B, int N, int D, const tvit_dropout* drop, tvit_stream_t stream);
+
+/* Backward of embed: g0 fp32 [B, n+1, D] (gradient of the residual stream at block 0's input)
+ *   gtok[T][b*n + i, :] = g0[b, 1+i, :] * dropout_mult      (input of the patch-embed weight-gradient GEMM)
+ *   R[i,:] = sum_b of the same (fp32)   dcls[:] = sum_b g0[b,0,:] * dropout_mult
+ * then tvit_pos_grad_reduce folds R [n, D] into dpos_k [Kp,D], dpos_f [Fp,D], dpos_t [Tp,D] and dbias [D]. */
+int tvit_embed_bwd_prep(const float* g0, int B, int n, int D, const tvit_dropout* drop, void* gtok, int dtype,
+                        float* R, float* dcls, tvit_stream_t stream);
+int tvit_pos_grad_reduce(const float* R, int Kp, int Fp, int Tp, int D, float* dpos_k, float* dpos_f,
+                         float* dpos_t, float* dbias, tvit_stream_t stream);
+
+/* y = x + alpha * y  style helpers are intentionally absent: everything else is fused above. */
+
+/* Fused AdamW step (torch.optim.AdamW semantics, train.py:154-156,227) over one flat
+ * fp32 parameter/gradient/moment range. step is 1-based. */
+int tvit_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+               float eps, float weight_decay, int step, float grad_scale, tvit_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVIT_H_ */

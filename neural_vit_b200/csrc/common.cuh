@@ -1,0 +1,165 @@
+// Shared device/host helpers for the Temporal 3D ViT sm_100a kernels.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "../../include/tvit.h"
+
+namespace tvit {
+
+// ---------------------------------------------------------------------------------------------
+// error reporting (tvit_last_error)
+// ---------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const char* fmt, ...);
+
+#define TVIT_CHECK_ARG(cond, ...)                                  \
+  do {                                                             \
+    if (!(cond)) return ::tvit::fail(TVIT_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define TVIT_CUDA_OK(expr)                                                                     \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ::tvit::fail(TVIT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                          __FILE__, __LINE__);                                                 \
+  } while (0)
+
+#define TVIT_LAUNCH_OK()                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = cudaGetLastError();                                                          \
+    if (_e != cudaSuccess)                                                                        \
+      return ::tvit::fail(TVIT_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                          __FILE__, __LINE__);                                                    \
+  } while (0)
+
+int num_sms();
+
+// ---------------------------------------------------------------------------------------------
+// activation element types: float (verification path) and bf16 (product path)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Act;
+template <>
+struct Act<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <>
+struct Act<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// 4 consecutive elements (16 B fp32 / 8 B bf16)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  uint2 r;
+  r.x = pack_bf16(v.x, v.y);
+  r.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// exact (erf) GELU and its derivative -- nn.GELU() default, reference model.py:137
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// ---------------------------------------------------------------------------------------------
+// counter-based dropout RNG: Philox4x32-7, 16 random bits per element, 8 elements per call.
+// keep(e) <=> bits16(e) >= thr16, thr16 = round(p * 65536).  A mask is a pure function of
+// (seed, site, element index), so forward and backward regenerate it without storing it.
+// ---------------------------------------------------------------------------------------------
+struct DropCfg {
+  unsigned long long seed;
+  unsigned int site;   // unique per dropout call site within one forward
+  unsigned int thr16;  // 0 => dropout disabled (identity)
+  float inv_keep;      // 1 / (1 - p)
+};
+
+__host__ __device__ __forceinline__ DropCfg make_drop(const tvit_dropout* d) {
+  DropCfg c;
+  c.seed = d ? d->seed : 0ull;
+  c.site = d ? d->site : 0u;
+  float p = d ? d->p : 0.f;
+  if (p <= 0.f) {
+    c.thr16 = 0;
+    c.inv_keep = 1.f;
+  } else {
+    unsigned int t = (unsigned int)(p * 65536.0f + 0.5f);
+    if (t > 65535u) t = 65535u;
+    c.thr16 = t;
+    c.inv_keep = 1.0f / (1.0f - (float)t * (1.0f / 65536.0f));
+  }
+  return c;
+}
+
+__device__ __forceinline__ uint4 philox4x32_7(unsigned long long seed, unsigned long long ctr, unsigned int site) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = site, c3 = 0x5eed5eedu;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// random 16-bit lanes for the 8 consecutive elements [8*g, 8*g+8)
+__device__ __forceinline__ void drop_bits8(const DropCfg& c, unsigned long long group, uint32_t out[4]) {
+  uint4 r = philox4x32_7(c.seed, group, c.site);
+  out[0] = r.x;
+  out[1] = r.y;
+  out[2] = r.z;
+  out[3] = r.w;
+}
+// multiplier (0 or 1/(1-p)) for a single element index
+__device__ __forceinline__ float drop_mult(const DropCfg& c, unsigned long long e) {
+  if (c.thr16 == 0) return 1.0f;
+  uint32_t w[4];
+  drop_bits8(c, e >> 3, w);
+  const unsigned int j = (unsigned int)(e & 7ull);
+  const uint32_t bits = (w[j >> 1] >> ((j & 1u) * 16u)) & 0xffffu;
+  return bits >= c.thr16 ? c.inv_keep : 0.0f;
+}
+
+}  // namespace tvit

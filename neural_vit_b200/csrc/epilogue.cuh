@@ -1,0 +1,223 @@
+// Fused GEMM epilogues shared by the tcgen05 GEMM (tc_gemm.cu) and the SIMT verification GEMM
+// (simt.cu).  One call handles 4 consecutive output columns of one row from fp32 accumulators.
+#pragma once
+#include "common.cuh"
+
+namespace tvit {
+
+struct EpiParams {
+  int M, N;
+  void* out;
+  long long ldo;
+  const float* bias;
+  void* aux;
+  long long ldaux;
+  const float* resid;
+  long long ldres;
+  const float* gamma;
+  const float* row_scale;
+  int rpg;
+  DropCfg drop;
+  const float* pos_k;
+  const float* pos_f;
+  const float* pos_t;
+  int Kp, Fp, Tp;
+  int vec_ok;   // N % 4 == 0 and every leading dimension % 4 == 0 -> 4-wide vector path is legal
+  int vec8_ok;  // same with 8 (16-byte bf16 accesses)
+};
+
+inline EpiParams make_epi_params(const tvit_gemm_args* a) {
+  EpiParams p;
+  p.M = a->M;
+  p.N = a->N;
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.bias = a->bias;
+  p.aux = a->aux;
+  p.ldaux = a->ldaux;
+  p.resid = a->resid;
+  p.ldres = a->ldres;
+  p.gamma = a->gamma;
+  p.row_scale = a->row_scale;
+  p.rpg = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.drop = make_drop(&a->drop);
+  p.pos_k = a->pos_k;
+  p.pos_f = a->pos_f;
+  p.pos_t = a->pos_t;
+  p.Kp = a->Kp;
+  p.Fp = a->Fp;
+  p.Tp = a->Tp;
+  p.vec_ok = (a->N % 4 == 0) && (a->ldo % 4 == 0) && (a->aux == nullptr || a->ldaux % 4 == 0) &&
+             (a->resid == nullptr || a->ldres % 4 == 0);
+  p.vec8_ok = (a->N % 8 == 0) && (a->ldo % 8 == 0) && (a->aux == nullptr || a->ldaux % 8 == 0);
+  return p;
+}
+
+__device__ __forceinline__ void drop_mult4e(const DropCfg& c, unsigned long long e, float m[4]) {
+  if (c.thr16 == 0) {
+    m[0] = m[1] = m[2] = m[3] = 1.0f;
+    return;
+  }
+  if ((e & 3ull) == 0ull) {
+    uint32_t w[4];
+    drop_bits8(c, e >> 3, w);
+    const int h = (int)((e >> 2) & 1ull) * 2;
+    m[0] = ((w[h] & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
+    m[1] = ((w[h] >> 16) >= c.thr16) ? c.inv_keep : 0.f;
+    m[2] = ((w[h + 1] & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
+    m[3] = ((w[h + 1] >> 16) >= c.thr16) ? c.inv_keep : 0.f;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = drop_mult(c, e + j);
+  }
+}
+
+// scalar element (used for ragged N, e.g. the 2-class logits)
+template <int EPI, typename T>
+__device__ __forceinline__ void epi_apply1(const EpiParams& p, int m, int n, float v) {
+  if (EPI == TVIT_EPI_STORE) {
+    if (p.bias) v += p.bias[n];
+    Act<T>::st((T*)p.out + m * p.ldo + n, v);
+  } else if (EPI == TVIT_EPI_BIAS_GELU) {
+    if (p.bias) v += p.bias[n];
+    Act<T>::st((T*)p.aux + m * p.ldaux + n, v);
+    Act<T>::st((T*)p.out + m * p.ldo + n, gelu_f(v) * drop_mult(p.drop, (unsigned long long)m * p.N + n));
+  } else if (EPI == TVIT_EPI_RESIDUAL) {
+    if (p.bias) v += p.bias[n];
+    v *= drop_mult(p.drop, (unsigned long long)m * p.N + n);
+    if (p.gamma) v *= p.gamma[n];
+    if (p.row_scale) v *= p.row_scale[m / p.rpg];
+    ((float*)p.out)[m * p.ldo + n] = p.resid[m * p.ldres + n] + v;
+  } else if (EPI == TVIT_EPI_GELU_BWD) {
+    const float h = Act<T>::ld((const T*)p.aux + m * p.ldaux + n);
+    Act<T>::st((T*)p.out + m * p.ldo + n, v * drop_mult(p.drop, (unsigned long long)m * p.N + n) * gelu_grad_f(h));
+  } else if (EPI == TVIT_EPI_ACCUM_F32) {
+    atomicAdd((float*)p.out + m * p.ldo + n, v);
+  } else if (EPI == TVIT_EPI_PATCH_EMBED) {
+    const int npatch = p.Kp * p.Fp * p.Tp;
+    const int b = m / npatch, i = m - b * npatch;
+    const int kp = i / (p.Fp * p.Tp), fp = (i / p.Tp) % p.Fp, tp = i % p.Tp;
+    const long long orow = (long long)b * (npatch + 1) + 1 + i;
+    if (p.bias) v += p.bias[n];
+    v += p.pos_k[(long long)kp * p.N + n] + p.pos_f[(long long)fp * p.N + n] + p.pos_t[(long long)tp * p.N + n];
+    v *= drop_mult(p.drop, (unsigned long long)orow * p.N + n);
+    ((float*)p.out)[orow * p.ldo + n] = v;
+  }
+}
+
+// 4 consecutive columns n0..n0+3 of row m (n0 % 4 == 0).  Falls back to scalars at a ragged edge.
+template <int EPI, typename T>
+__device__ __forceinline__ void epi_apply4(const EpiParams& p, int m, int n0, float4 v) {
+  if (!(p.vec_ok && n0 + 4 <= p.N)) {
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n0 + j < p.N) epi_apply1<EPI, T>(p, m, n0 + j, vv[j]);
+    return;
+  }
+  if (EPI == TVIT_EPI_STORE) {
+    if (p.bias) {
+      const float4 b = ld4(p.bias + n0);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    st4((T*)p.out + m * p.ldo + n0, v);
+  } else if (EPI == TVIT_EPI_BIAS_GELU) {
+    if (p.bias) {
+      const float4 b = ld4(p.bias + n0);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    st4((T*)p.aux + m * p.ldaux + n0, v);
+    float mlt[4];
+    drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, mlt);
+    st4((T*)p.out + m * p.ldo + n0,
+        make_float4(gelu_f(v.x) * mlt[0], gelu_f(v.y) * mlt[1], gelu_f(v.z) * mlt[2], gelu_f(v.w) * mlt[3]));
+  } else if (EPI == TVIT_EPI_RESIDUAL) {
+    if (p.bias) {
+      const float4 b = ld4(p.bias + n0);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    float mlt[4];
+    drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, mlt);
+    float rs = p.row_scale ? p.row_scale[m / p.rpg] : 1.0f;
+    float4 g = p.gamma ? ld4(p.gamma + n0) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 r = ld4(p.resid + m * p.ldres + n0);
+    st4((float*)p.out + m * p.ldo + n0,
+        make_float4(r.x + rs * g.x * v.x * mlt[0], r.y + rs * g.y * v.y * mlt[1], r.z + rs * g.z * v.z * mlt[2],
+                    r.w + rs * g.w * v.w * mlt[3]));
+  } else if (EPI == TVIT_EPI_GELU_BWD) {
+    const float4 h = ld4((const T*)p.aux + m * p.ldaux + n0);
+    float mlt[4];
+    drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, mlt);
+    st4((T*)p.out + m * p.ldo + n0,
+        make_float4(v.x * mlt[0] * gelu_grad_f(h.x), v.y * mlt[1] * gelu_grad_f(h.y), v.z * mlt[2] * gelu_grad_f(h.z),
+                    v.w * mlt[3] * gelu_grad_f(h.w)));
+  } else if (EPI == TVIT_EPI_ACCUM_F32) {
+    float* o = (float*)p.out + m * p.ldo + n0;
+    atomicAdd(o + 0, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+  } else if (EPI == TVIT_EPI_PATCH_EMBED) {
+    const int npatch = p.Kp * p.Fp * p.Tp;
+    const int b = m / npatch, i = m - b * npatch;
+    const int kp = i / (p.Fp * p.Tp), fp = (i / p.Tp) % p.Fp, tp = i % p.Tp;
+    const long long orow = (long long)b * (npatch + 1) + 1 + i;
+    if (p.bias) {
+      const float4 bb = ld4(p.bias + n0);
+      v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+    }
+    const float4 a = ld4(p.pos_k + (long long)kp * p.N + n0);
+    const float4 c = ld4(p.pos_f + (long long)fp * p.N + n0);
+    const float4 d = ld4(p.pos_t + (long long)tp * p.N + n0);
+    float mlt[4];
+    drop_mult4e(p.drop, (unsigned long long)orow * p.N + n0, mlt);
+    st4((float*)p.out + orow * p.ldo + n0,
+        make_float4((v.x + a.x + c.x + d.x) * mlt[0], (v.y + a.y + c.y + d.y) * mlt[1],
+                    (v.z + a.z + c.z + d.z) * mlt[2], (v.w + a.w + c.w + d.w) * mlt[3]));
+  }
+}
+
+// 8 consecutive columns (n0 % 8 == 0) of row m: 16-byte bf16 accesses for the act-output epilogues of
+// the tensor-core path; everything else is two 4-wide calls.
+template <int EPI, typename T>
+__device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, const float (&v)[8]) {
+  constexpr bool kWide = (sizeof(T) == 2) &&
+                         (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_GELU_BWD);
+  if (kWide && p.vec8_ok && n0 + 8 <= p.N) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = v[j];
+    if (EPI != TVIT_EPI_GELU_BWD && p.bias) {
+      const float4 b0 = ld4(p.bias + n0), b1 = ld4(p.bias + n0 + 4);
+      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    }
+    if (EPI == TVIT_EPI_STORE) {
+      uint4 o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+      *reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + m * p.ldo + n0) = o;
+      return;
+    }
+    float ml[8];
+    drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, ml);
+    drop_mult4e(p.drop, (unsigned long long)m * p.N + n0 + 4, ml + 4);
+    if (EPI == TVIT_EPI_BIAS_GELU) {
+      uint4 h = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+      *reinterpret_cast<uint4*>((__nv_bfloat16*)p.aux + m * p.ldaux + n0) = h;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = gelu_f(x[j]) * ml[j];
+    } else {  // GELU_BWD
+      const uint4 h = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.aux + m * p.ldaux + n0);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+        x[2 * j] = x[2 * j] * ml[2 * j] * gelu_grad_f(f.x);
+        x[2 * j + 1] = x[2 * j + 1] * ml[2 * j + 1] * gelu_grad_f(f.y);
+      }
+    }
+    uint4 o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    *reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + m * p.ldo + n0) = o;
+    return;
+  }
+  epi_apply4<EPI, T>(p, m, n0, make_float4(v[0], v[1], v[2], v[3]));
+  if (n0 + 4 < p.N) epi_apply4<EPI, T>(p, m, n0 + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+
+}  // namespace tvit

@@ -1,0 +1,372 @@
+// tcgen05 GEMM for sm_100a: C[M,N] = op(A) op(B)^T (bf16 operands, fp32 accumulate in TMEM) with the
+// fused epilogues of epilogue.cuh.
+//
+// Persistent, warp-specialised:
+//   warp 0   TMA producer    (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1   MMA issuer      (one elected thread: tcgen05.mma cta_group::1, 128 x BN x 16 per instruction)
+//   warp 2   TMEM allocator  (2 accumulator stages x BN fp32 columns)
+//   warps 4-7 epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global), overlapped with
+//                            the next tile's main loop through the double-buffered TMEM accumulator.
+// Operand layouts:
+//   K-major (trans == 0): box {64 k, rows} -> rows of 128 B, 8-row swizzle atoms (SBO 1024).
+//   MN-major (trans == 1, weight-gradient GEMMs with K = tokens): boxes {64 mn, 64 k}; 64-wide MN blocks
+//   are LBO = 8192 B apart, 8-k-row groups SBO = 1024 B apart.
+// Work items = m_tile x n_tile x k_split, static round-robin over the persistent CTAs.
+#include <cstdlib>
+
+#include "epilogue.cuh"
+#include "tc_common.cuh"
+
+namespace tvit {
+
+// ------------------------------------------------------------------------------------------
+// tensor-map creation through the driver entry point (no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(TVIT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (((uintptr_t)base & 15u) != 0) return fail(TVIT_ERR_BAD_ARG, "TMA base address %p not 16-byte aligned", base);
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      if (strides_bytes[i - 1] % 16 != 0)
+        return fail(TVIT_ERR_BAD_ARG, "TMA stride %llu bytes not a multiple of 16 (leading dimension %% 8 != 0)",
+                    (unsigned long long)strides_bytes[i - 1]);
+      gstr[i - 1] = strides_bytes[i - 1];
+    }
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TVIT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return TVIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmShape {
+  int M, N, K;          // logical GEMM shape (K = reduction)
+  int m_tiles, n_tiles; // output tiles
+  int k_blocks;         // ceil(K / 64)
+  int splits;           // K splits (>= 1), every split non-empty
+  int kb_per_split;
+  // UMMA smem-descriptor geometry (bytes); runtime so a debug override can sweep it (TVIT_MN_DESC)
+  uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape sh,
+               EpiParams ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
+  uint64_t* tempty_bar = bars + 2 * Cfg::kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_work = sh.m_tiles * sh.n_tiles * sh.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int tile = w / sh.splits, split = w - tile * sh.splits;
+        const int m0 = (tile / sh.n_tiles) * kBM, n0 = (tile % sh.n_tiles) * BN;
+        const int kb0 = split * sh.kb_per_split;
+        const int kb1 = min(kb0 + sh.kb_per_split, sh.k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBM / 64; ++j)
+              tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, kb * kBK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * kBK);
+          }
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint32_t a_lbo = sh.a_lbo, b_lbo = sh.b_lbo, a_sbo = sh.a_sbo, b_sbo = sh.b_sbo;
+      const uint32_t a_kstep = sh.a_kstep, b_kstep = sh.b_kstep;  // bytes per UMMA_K = 16
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+        const int tile = w / sh.splits, split = w - tile * sh.splits;
+        const int kb0 = split * sh.kb_per_split;
+        const int kb1 = min(kb0 + sh.kb_per_split, sh.k_blocks);
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
+            const uint64_t db = umma_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
+            umma_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
+    int it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const int tile = w / sh.splits;
+      const int m0 = (tile / sh.n_tiles) * kBM, n0 = (tile % sh.n_tiles) * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 >= sh.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (m < sh.M) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[8 * j + t]);
+            epi_apply8<EPI, __nv_bfloat16>(ep, m, n0 + c * 32 + 8 * j, v);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host launch
+// ------------------------------------------------------------------------------------------
+template <int BN, bool MN, int EPI>
+static int launch_tc(const tvit_gemm_args* a, const GemmShape& sh, const EpiParams& ep, cudaStream_t s) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = tc_gemm_kernel<BN, MN, MN, EPI>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+                cudaGetErrorString(attr_err));
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!MN) {
+    // A [M,K] K contiguous; B [N,K] K contiguous
+    const uint64_t da[2] = {(uint64_t)a->K, (uint64_t)a->M}, sa[1] = {(uint64_t)a->lda * 2};
+    const uint32_t ba[2] = {kBK, kBM};
+    if ((rc = make_tmap_bf16(&tmA, a->A, 2, da, sa, ba)) != TVIT_OK) return rc;
+    const uint64_t db[2] = {(uint64_t)a->K, (uint64_t)a->N}, sb[1] = {(uint64_t)a->ldb * 2};
+    const uint32_t bb[2] = {kBK, (uint32_t)BN};
+    if ((rc = make_tmap_bf16(&tmB, a->B, 2, db, sb, bb)) != TVIT_OK) return rc;
+  } else {
+    // A stored [K, M] (M contiguous); B stored [K, N] (N contiguous)
+    const uint64_t da[2] = {(uint64_t)a->M, (uint64_t)a->K}, sa[1] = {(uint64_t)a->lda * 2};
+    const uint32_t ba[2] = {64, kBK};
+    if ((rc = make_tmap_bf16(&tmA, a->A, 2, da, sa, ba)) != TVIT_OK) return rc;
+    const uint64_t db[2] = {(uint64_t)a->N, (uint64_t)a->K}, sb[1] = {(uint64_t)a->ldb * 2};
+    const uint32_t bb[2] = {64, kBK};
+    if ((rc = make_tmap_bf16(&tmB, a->B, 2, db, sb, bb)) != TVIT_OK) return rc;
+  }
+  const int total = sh.m_tiles * sh.n_tiles * sh.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, sh, ep);
+  TVIT_LAUNCH_OK();
+  return TVIT_OK;
+}
+
+template <int BN>
+static int dispatch_epi(const tvit_gemm_args* a, const GemmShape& sh, const EpiParams& ep, cudaStream_t s) {
+  const bool mn = a->trans_a != 0;
+  if (mn) {
+    if (a->epilogue != TVIT_EPI_ACCUM_F32)
+      return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 gemm: transposed operands only with the ACCUM_F32 epilogue");
+    return launch_tc<BN, true, TVIT_EPI_ACCUM_F32>(a, sh, ep, s);
+  }
+  switch (a->epilogue) {
+    case TVIT_EPI_STORE: return launch_tc<BN, false, TVIT_EPI_STORE>(a, sh, ep, s);
+    case TVIT_EPI_BIAS_GELU: return launch_tc<BN, false, TVIT_EPI_BIAS_GELU>(a, sh, ep, s);
+    case TVIT_EPI_RESIDUAL: return launch_tc<BN, false, TVIT_EPI_RESIDUAL>(a, sh, ep, s);
+    case TVIT_EPI_GELU_BWD: return launch_tc<BN, false, TVIT_EPI_GELU_BWD>(a, sh, ep, s);
+    case TVIT_EPI_PATCH_EMBED: return launch_tc<BN, false, TVIT_EPI_PATCH_EMBED>(a, sh, ep, s);
+    case TVIT_EPI_ACCUM_F32: return launch_tc<BN, false, TVIT_EPI_ACCUM_F32>(a, sh, ep, s);
+    default: return fail(TVIT_ERR_BAD_ARG, "gemm: unknown epilogue %d", a->epilogue);
+  }
+}
+
+int tc_gemm(const tvit_gemm_args* a, cudaStream_t s) {
+  if (a->dtype != TVIT_BF16) return fail(TVIT_ERR_BAD_ARG, "tcgen05 gemm needs bf16 operands");
+  if (a->trans_a != a->trans_b)
+    return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 gemm: supported layouts are (trans_a,trans_b) = (0,0) or (1,1)");
+  if (a->lda % 8 != 0 || a->ldb % 8 != 0)
+    return fail(TVIT_ERR_BAD_ARG, "tcgen05 gemm: lda/ldb must be multiples of 8 (lda=%lld ldb=%lld)", a->lda, a->ldb);
+
+  // pick BN in {128,192,256} minimising padded N; ties -> larger tile
+  int best_bn = 128;
+  long long best_pad = -1;
+  const int cands[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long long pad = (long long)((a->N + bn - 1) / bn) * bn;
+    if (best_pad < 0 || pad < best_pad) {
+      best_pad = pad;
+      best_bn = bn;
+    }
+  }
+  GemmShape sh;
+  sh.M = a->M;
+  sh.N = a->N;
+  sh.K = a->K;
+  sh.m_tiles = (a->M + kBM - 1) / kBM;
+  sh.n_tiles = (a->N + best_bn - 1) / best_bn;
+  sh.k_blocks = (a->K + kBK - 1) / kBK;
+  int splits = 1;
+  if (a->epilogue == TVIT_EPI_ACCUM_F32) {
+    splits = a->split_k > 0 ? a->split_k : num_sms() / (sh.m_tiles * sh.n_tiles);
+    if (splits < 1) splits = 1;
+    if (splits > sh.k_blocks) splits = sh.k_blocks;
+  }
+  sh.kb_per_split = (sh.k_blocks + splits - 1) / splits;
+  sh.splits = (sh.k_blocks + sh.kb_per_split - 1) / sh.kb_per_split;
+  // K-major: 8-row atoms 1024 B apart (SBO), 32 B per 16-element k step inside the 128 B swizzle row.
+  // MN-major: 64-wide MN blocks 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), 16 k rows = 2048 B.
+  const bool mn = a->trans_a != 0;
+  sh.a_lbo = sh.b_lbo = mn ? 8192u : 0u;
+  sh.a_sbo = sh.b_sbo = 1024u;
+  sh.a_kstep = sh.b_kstep = mn ? 2048u : 32u;
+  if (mn) {
+    if (const char* dbg = getenv("TVIT_MN_DESC")) {  // debug only: "lbo,sbo,kstep"
+      unsigned l = 0, sb = 0, ks = 0;
+      if (sscanf(dbg, "%u,%u,%u", &l, &sb, &ks) == 3) {
+        sh.a_lbo = sh.b_lbo = l;
+        sh.a_sbo = sh.b_sbo = sb;
+        sh.a_kstep = sh.b_kstep = ks;
+      }
+    }
+  }
+  const EpiParams ep = make_epi_params(a);
+  switch (best_bn) {
+    case 256: return dispatch_epi<256>(a, sh, ep, s);
+    case 192: return dispatch_epi<192>(a, sh, ep, s);
+    default: return dispatch_epi<128>(a, sh, ep, s);
+  }
+}
+
+}  // namespace tvit

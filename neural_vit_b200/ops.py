@@ -1,0 +1,159 @@
+"""Thin tensor-level wrappers over the C ABI (include/tvit.h).
+
+Every function takes CUDA tensors allocated by PyTorch, passes raw device pointers and the current
+CUDA stream to libtvit_b200.so, and raises RuntimeError on any non-zero return code.  No arithmetic
+happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+DropSpec = Optional[Tuple[int, int, float]]  # (seed, site, p)
+
+_TORCH_DTYPE = {L.F32: torch.float32, L.BF16: torch.bfloat16}
+
+
+def torch_dtype(code: int) -> torch.dtype:
+    return _TORCH_DTYPE[code]
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _drop(spec: DropSpec) -> L.Dropout:
+    if spec is None:
+        return L.Dropout(0, 0, 0.0)
+    seed, site, p = spec
+    return L.Dropout(int(seed), int(site), float(p))
+
+
+def _drop_ptr(spec: DropSpec):
+    return ctypes.byref(_drop(spec))
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the B200 kernels have no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+
+
+def gemm(engine: int, dtype: int, a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, epilogue: int,
+         out: torch.Tensor, lda: Optional[int] = None, ldb: Optional[int] = None, ldo: Optional[int] = None,
+         trans_a: bool = False, trans_b: bool = False, bias=None, aux=None, resid=None, gamma=None, row_scale=None,
+         rows_per_group: int = 0, drop: DropSpec = None, pos=None, grid3=None, split_k: int = 0) -> None:
+    """C[M,N] = op(A) op(B)^T with a fused epilogue (see tvit_gemm in include/tvit.h)."""
+    td = torch_dtype(dtype)
+    _req(a, td, "gemm A")
+    _req(b, td, "gemm B")
+    args = L.GemmArgs()
+    args.engine, args.dtype = engine, dtype
+    args.trans_a, args.trans_b = int(trans_a), int(trans_b)
+    args.M, args.N, args.K = M, N, K
+    args.A, args.lda = a.data_ptr(), (lda if lda is not None else (M if trans_a else K))
+    args.B, args.ldb = b.data_ptr(), (ldb if ldb is not None else (N if trans_b else K))
+    args.epilogue = epilogue
+    args.out, args.ldo = out.data_ptr(), (ldo if ldo is not None else N)
+    args.bias = _ptr(bias)
+    args.aux, args.ldaux = _ptr(aux), N
+    args.resid, args.ldres = _ptr(resid), N
+    args.gamma = _ptr(gamma)
+    args.row_scale = _ptr(row_scale)
+    args.rows_per_group = rows_per_group
+    args.drop = _drop(drop)
+    if pos is not None:
+        args.pos_k, args.pos_f, args.pos_t = (p.data_ptr() for p in pos)
+        args.Kp, args.Fp, args.Tp = grid3
+    args.split_k = split_k
+    L.check(L.load().tvit_gemm(ctypes.byref(args), _stream()), "tvit_gemm")
+
+
+def attn_fwd(engine, dtype, qkv, out, lse, B, N, H, hd, drop: DropSpec = None) -> None:
+    L.check(L.load().tvit_attn_fwd(engine, dtype, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, hd,
+                                   _drop_ptr(drop), _stream()), "tvit_attn_fwd")
+
+
+def attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, B, N, H, hd, drop: DropSpec = None) -> None:
+    lib = L.load()
+    nbytes = int(lib.tvit_attn_bwd_workspace_bytes(engine, dtype, B, N, H, hd))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qkv.device)
+    L.check(lib.tvit_attn_bwd(engine, dtype, qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                              dqkv.data_ptr(), ws.data_ptr(), nbytes, B, N, H, hd, _drop_ptr(drop), _stream()),
+            "tvit_attn_bwd")
+
+
+def attn_probs(dtype, qkv, probs, B, N, H, hd) -> None:
+    L.check(L.load().tvit_attn_probs(dtype, qkv.data_ptr(), probs.data_ptr(), B, N, H, hd, _stream()),
+            "tvit_attn_probs")
+
+
+def im2col(x, cols, dtype, B, K, F, T, pk, pf, pt) -> None:
+    _req(x, torch.float32, "im2col x")
+    L.check(L.load().tvit_im2col(x.data_ptr(), cols.data_ptr(), dtype, B, K, F, T, pk, pf, pt, _stream()),
+            "tvit_im2col")
+
+
+def ln_fwd(x, x_row_stride, weight, bias, y, dtype, mean, rstd, rows, D, eps=1e-5) -> None:
+    L.check(L.load().tvit_ln_fwd(x.data_ptr(), x_row_stride, weight.data_ptr(), bias.data_ptr(), y.data_ptr(), dtype,
+                                 _ptr(mean), _ptr(rstd), rows, D, eps, _stream()), "tvit_ln_fwd")
+
+
+def ln_bwd(dy, dtype, x, x_row_stride, mean, rstd, weight, g_res, dx, dx_row_stride, dweight, dbias, rows, D, *,
+           gp=None, row_scale=None, rows_per_group=0, drop: DropSpec = None, gp_colsum=None) -> None:
+    L.check(L.load().tvit_ln_bwd(dy.data_ptr(), dtype, x.data_ptr(), x_row_stride, mean.data_ptr(), rstd.data_ptr(),
+                                 weight.data_ptr(), _ptr(g_res), dx.data_ptr(), dx_row_stride, _ptr(dweight),
+                                 _ptr(dbias), _ptr(gp), _ptr(row_scale), rows_per_group, _drop_ptr(drop),
+                                 _ptr(gp_colsum), rows, D, _stream()), "tvit_ln_bwd")
+
+
+def branch_grad_prep(g, rows, D, row_scale, rows_per_group, drop: DropSpec, gp, dtype, colsum) -> None:
+    L.check(L.load().tvit_branch_grad_prep(g.data_ptr(), rows, D, _ptr(row_scale), rows_per_group, _drop_ptr(drop),
+                                           gp.data_ptr(), dtype, _ptr(colsum), _stream()), "tvit_branch_grad_prep")
+
+
+def colsum(x, dtype, rows, C, ld, out) -> None:
+    L.check(L.load().tvit_colsum(x.data_ptr(), dtype, rows, C, ld, out.data_ptr(), _stream()), "tvit_colsum")
+
+
+def cast_weight(w, R, C, row_scale, out, out_t, dtype) -> None:
+    L.check(L.load().tvit_cast_weight(w.data_ptr(), R, C, _ptr(row_scale), _ptr(out), _ptr(out_t), dtype, _stream()),
+            "tvit_cast_weight")
+
+
+def ls_finalize(G, W, gamma, bias, cs, dW, dgamma, dbias, R, C) -> None:
+    L.check(L.load().tvit_ls_finalize(G.data_ptr(), _ptr(W), _ptr(gamma), _ptr(bias), cs.data_ptr(), dW.data_ptr(),
+                                      _ptr(dgamma), _ptr(dbias), R, C, _stream()), "tvit_ls_finalize")
+
+
+def cls_rows(cls, h, B, N, D, drop: DropSpec) -> None:
+    L.check(L.load().tvit_cls_rows(cls.data_ptr(), h.data_ptr(), B, N, D, _drop_ptr(drop), _stream()),
+            "tvit_cls_rows")
+
+
+def embed_bwd_prep(g0, B, n, D, drop: DropSpec, gtok, dtype, R, dcls) -> None:
+    L.check(L.load().tvit_embed_bwd_prep(g0.data_ptr(), B, n, D, _drop_ptr(drop), gtok.data_ptr(), dtype,
+                                         R.data_ptr(), dcls.data_ptr(), _stream()), "tvit_embed_bwd_prep")
+
+
+def pos_grad_reduce(R, Kp, Fp, Tp, D, dpk, dpf, dpt, dbias) -> None:
+    L.check(L.load().tvit_pos_grad_reduce(R.data_ptr(), Kp, Fp, Tp, D, dpk.data_ptr(), dpf.data_ptr(),
+                                          dpt.data_ptr(), dbias.data_ptr(), _stream()), "tvit_pos_grad_reduce")
+
+
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> None:
+    L.check(L.load().tvit_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
+                                eps, weight_decay, step, grad_scale, _stream()), "tvit_adamw")

