@@ -28,8 +28,27 @@ def _newest_header() -> float:
     return t
 
 
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    files.append(os.path.join(os.path.dirname(HERE), "include", "tvit.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    digest = _source_hash()
+    stamp = LIB + ".hash"
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        if verbose:
+            print("up to date", LIB)
+        return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
     hdr_t = _newest_header()
     jobs = []
@@ -60,6 +79,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print("linked", LIB)
+    with open(stamp, "w") as fh:
+        fh.write(digest)
     return LIB
 
 

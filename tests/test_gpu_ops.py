@@ -15,8 +15,8 @@ from tests.conftest import rel_err
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-ENGINES = [(L.ENGINE_SIMT, L.F32, "simt-f32"), (L.ENGINE_SIMT, L.BF16, "simt-bf16"),
-           (L.ENGINE_TCGEN05, L.BF16, "tc-bf16")]
+ENGINES = [(L.ENGINE_SIMT, L.F32, "simt_f32"), (L.ENGINE_SIMT, L.BF16, "simt_bf16"),
+           (L.ENGINE_TCGEN05, L.BF16, "tc_bf16")]
 
 
 def _tol(dtype):

@@ -64,9 +64,24 @@ def gemm_tn(M, N, K, engine=L.ENGINE_TCGEN05):
     return out, a.double().T @ b.double()
 
 
+def sweep():
+    print("== MN-major descriptor sweep (lbo,sbo,kstep)")
+    for lbo in (8192, 1024, 128, 0):
+        for sbo in (1024, 8192, 128):
+            for ks in (2048, 32, 256):
+                os.environ["TVIT_MN_DESC"] = f"{lbo},{sbo},{ks}"
+                r = run(lambda: gemm_tn(128, 128, 128), f"sweep {lbo},{sbo},{ks}")
+                if r is not None:
+                    print(f"  lbo={lbo:5d} sbo={sbo:5d} kstep={ks:5d} rel_err={rel(*r):.3e}", flush=True)
+    os.environ.pop("TVIT_MN_DESC", None)
+
+
 def main():
     print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0), flush=True)
     L.require_device(0)
+    if "--sweep-only" in sys.argv:
+        sweep()
+        return
     print("== K-major (NT) tcgen05 GEMM")
     for (M, N, K) in [(128, 128, 64), (128, 128, 128), (128, 256, 64), (256, 192, 256), (300, 384, 384),
                       (4098, 1152, 384), (1000, 1536, 384), (777, 384, 1536)]:
@@ -87,16 +102,6 @@ def main():
         print(f"TN {M:5d}x{N:5d}x{K:5d} rel_err={e:.3e} {'OK' if e < 1e-3 else 'BAD'}", flush=True)
         if e >= 1e-3 and M <= 256:
             print(errmap(*r))
-    if "--sweep" in sys.argv:
-        print("== MN-major descriptor sweep (lbo,sbo,kstep)")
-        for lbo in (8192, 1024, 128, 0):
-            for sbo in (1024, 8192, 128):
-                for ks in (2048, 32, 256):
-                    os.environ["TVIT_MN_DESC"] = f"{lbo},{sbo},{ks}"
-                    r = run(lambda: gemm_tn(128, 128, 128), f"sweep {lbo},{sbo},{ks}")
-                    if r is not None:
-                        print(f"  lbo={lbo:5d} sbo={sbo:5d} kstep={ks:5d} rel_err={rel(*r):.3e}", flush=True)
-        os.environ.pop("TVIT_MN_DESC", None)
 
     print("== timing (CUDA events, 20 iters after 5 warm-up)")
     def timeit(fn, iters=20):
