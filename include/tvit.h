@@ -112,7 +112,7 @@ int tvit_gemm(const tvit_gemm_args* args, tvit_stream_t stream);
  * no B*H*N*N tensor is materialised; only the per-row log-sum-exp is kept for backward.
  *   qkv : [B*N, 3*H*hd] act, columns ordered [q(all heads) | k | v], head h = cols h*hd..(h+1)*hd
  *   out : [B*N, H*hd] act (token-major, heads merged)       lse : [B, H, N] fp32 (natural log)
- * Dropout on the probabilities: element index = ((b*H + h)*N + q)*N + k.
+ * Dropout on the probabilities: element index = ((b*H + h)*N + q)*Np + k, Np = N rounded up to 8.
  * Replaces model.py:108-115 (reshape/permute, q@k^T*scale, softmax, attn_drop, @v, transpose).
  * ------------------------------------------------------------------------------------------- */
 int tvit_attn_fwd(int engine, int dtype, const void* qkv, void* out, float* lse, int B, int N, int H, int hd,

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) simt_attn_fwd_kernel(const T* __restrict_
     o[j] = 0.f;
   }
   float mx = -INFINITY, l = 0.f;
-  const unsigned long long rowe = (((unsigned long long)b * H + h) * N + q) * (unsigned long long)N;
+  const unsigned long long rowe = (((unsigned long long)b * H + h) * N + q) * (unsigned long long)((N + 7) & ~7);
   for (int k = 0; k < N; ++k) {
     const T* kr = base + (long long)k * 3 * D + D + h * hd;
     const T* vr = base + (long long)k * 3 * D + 2 * D + h * hd;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128) simt_attn_bwd_kernel(const T* __restrict_
   }
   dsum = warp_sum(dsum);
   const float L = lse[((long long)b * H + h) * N + q];
-  const unsigned long long rowe = (((unsigned long long)b * H + h) * N + q) * (unsigned long long)N;
+  const unsigned long long rowe = (((unsigned long long)b * H + h) * N + q) * (unsigned long long)((N + 7) & ~7);
   for (int k = 0; k < N; ++k) {
     const T* kr = base + (long long)k * 3 * D + D + h * hd;
     const T* vr = base + (long long)k * 3 * D + 2 * D + h * hd;

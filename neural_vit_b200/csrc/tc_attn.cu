@@ -1,0 +1,263 @@
+// Fused flash-style multi-head self-attention for sm_100a (head_dim 64, bf16 operands, fp32 softmax).
+// Forward: one CTA per (128-query tile, head, sample).
+//   warp 4   TMA producer: Q tile once, then K_j / V_j tiles (128 x 64 bf16, 128B swizzle) into a 2-stage ring
+//   warp 5   MMA issuer  : S_j = Q K_j^T (tcgen05.mma SS, 128x128x64) and O += P_j V_j (tcgen05.mma TS: P from
+//                          TMEM, V as an MN-major smem operand, 128x64x128); also owns the TMEM allocation
+//   warps 0-3 softmax    : thread == query row; S row from TMEM (tcgen05.ld), online softmax with running
+//                          max / sum in registers, P -> bf16 -> TMEM (tcgen05.st), conditional O rescale
+// The S_{j+1} MMA is issued as soon as S_j has been read into registers, so it overlaps softmax_j; two
+// CTAs per SM (80 KB smem, 256 TMEM columns each) overlap one CTA's exponentials with the other's MMAs.
+// Only the row log-sum-exp is kept for backward.  qkv is read in place through a 3-D tensor map
+// {3D, N, B} (rows past N are zero-filled by TMA), the output is written token-major [B*N, H*64].
+#include "tc_common.cuh"
+
+namespace tvit {
+
+constexpr int kHd = 64;
+constexpr int kTile = 128;
+constexpr int kAttnFwdThreads = 192;
+constexpr int kTileBytes = kTile * kHd * 2;  // 16384
+
+// attention-dropout element index: row-major over (b, h, q, k) with the k extent padded to a multiple of 8
+// so that a thread's 128 consecutive keys start on a Philox group boundary (same definition in simt.cu)
+__host__ __device__ __forceinline__ unsigned long long attn_drop_row_base(int b, int H, int h, int N, int q) {
+  const unsigned long long npad = (unsigned long long)((N + 7) & ~7);
+  return (((unsigned long long)b * H + h) * N + q) * npad;
+}
+
+struct AttnFwdSmem {
+  uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, pv_done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kAttnFwdThreads, 2)
+tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
+                   float* __restrict__ lse, int N, int H, float scale_log2, DropCfg drop) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + kTileBytes;  // stage s: K at sKV + s*2*kTileBytes, V right after K
+  AttnFwdSmem* sm = reinterpret_cast<AttnFwdSmem*>(smem + 5 * kTileBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * kHd;
+  const int q0 = qt * kTile;
+  const int nkv = (N + kTile - 1) / kTile;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sm->q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm->kv_full[i], 1);
+      mbar_init(&sm->kv_empty[i], 1);
+    }
+    mbar_init(&sm->s_full, 1);
+    mbar_init(&sm->s_free, 128);
+    mbar_init(&sm->p_full, 128);
+    mbar_init(&sm->pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(&sm->tmem_base, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  const uint32_t tS = tmem, tO = tmem + 128, tP = tmem + 192;
+
+  if (warp == 4) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      mbar_expect_tx(&sm->q_full, kTileBytes);
+      tma_load_3d(sQ, &tm_qkv, &sm->q_full, h * kHd, q0, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&sm->kv_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&sm->kv_full[st], 2 * kTileBytes);
+        uint8_t* sK = sKV + st * 2 * kTileBytes;
+        tma_load_3d(sK, &tm_qkv, &sm->kv_full[st], D + h * kHd, j * kTile, b);
+        tma_load_3d(sK + kTileBytes, &tm_qkv, &sm->kv_full[st], 2 * D + h * kHd, j * kTile, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B = V: MN-major
+      const uint32_t aQ = smem_u32(sQ);
+      mbar_wait(&sm->q_full, 0);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&sm->kv_full[st], ((uint32_t)j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sKV + st * 2 * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k)
+          umma_ss(tS, umma_smem_desc(aQ + k * 32, 0, 1024), umma_smem_desc(aK + k * 32, 0, 1024), idesc_s,
+                  k > 0 ? 1u : 0u);
+        tc_commit(&sm->s_full);
+      };
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        if (j + 1 < nkv) {
+          mbar_wait(&sm->s_free, (uint32_t)j & 1u);  // softmax_j holds S_j in registers
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait(&sm->p_full, (uint32_t)j & 1u);  // P_j in TMEM, O rescaled
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sKV + st * 2 * kTileBytes + kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k)
+          umma_ts(tO, tP + k * 8, umma_smem_desc(aV + k * 2048, 16384, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&sm->kv_empty[st]);
+        tc_commit(&sm->pv_done);
+      }
+    }
+  } else {
+    // ============================ softmax warps ============================
+    const int r = warp * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int q = q0 + r;
+    float m2 = -INFINITY, l = 0.f;
+    const unsigned long long rowe = attn_drop_row_base(b, H, h, N, q < N ? q : 0);
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&sm->s_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      uint32_t sreg[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS + lane_off + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sm->s_free);
+
+      const int valid = N - j * kTile;  // keys beyond N are masked
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) {
+        float v = __uint_as_float(sreg[c]) * scale_log2;
+        v = (c < valid) ? v : -INFINITY;
+        sreg[c] = __float_as_uint(v);
+        mx = fmaxf(mx, v);
+      }
+      const float m_new = fmaxf(m2, mx);
+      const float corr = exp2f(m2 - m_new);
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) {
+        const float p = exp2f(__uint_as_float(sreg[c]) - m_new);
+        rs += p;
+        sreg[c] = __float_as_uint(p);
+      }
+      l = l * corr + rs;
+      if (drop.thr16 != 0) {
+        const unsigned long long g0 = (rowe + (unsigned long long)j * kTile) >> 3;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          uint32_t w[4];
+          drop_bits8(drop, g0 + g, w);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const uint32_t bits = (w[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
+            const float p = __uint_as_float(sreg[g * 8 + t]);
+            sreg[g * 8 + t] = __float_as_uint(bits >= drop.thr16 ? p * drop.inv_keep : 0.f);
+          }
+        }
+      }
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) pk[c] = pack_bf16(__uint_as_float(sreg[2 * c]), __uint_as_float(sreg[2 * c + 1]));
+
+      if (j > 0) {
+        mbar_wait(&sm->pv_done, (uint32_t)(j - 1) & 1u);  // O and the P buffer are free again
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, m_new > m2)) {  // warp-uniform: rescale the running output
+          uint32_t o[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(tO + lane_off + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * corr);
+            tmem_st32(tO + lane_off + c * 32, o);
+          }
+        }
+      }
+      m2 = m_new;
+      tmem_st32(tP + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      tmem_st32(tP + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&sm->p_full);
+    }
+    // ---- epilogue: O / l -> bf16, token-major store; LSE ----
+    mbar_wait(&sm->pv_done, (uint32_t)(nkv - 1) & 1u);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = out + ((long long)b * N + q) * D + h * kHd;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + lane_off + c * 32, o);
+      tmem_ld_wait();
+      if (q < N) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[8 * t + 0]) * inv, __uint_as_float(o[8 * t + 1]) * inv);
+          v.y = pack_bf16(__uint_as_float(o[8 * t + 2]) * inv, __uint_as_float(o[8 * t + 3]) * inv);
+          v.z = pack_bf16(__uint_as_float(o[8 * t + 4]) * inv, __uint_as_float(o[8 * t + 5]) * inv);
+          v.w = pack_bf16(__uint_as_float(o[8 * t + 6]) * inv, __uint_as_float(o[8 * t + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + 8 * t) = v;
+        }
+      }
+    }
+    if (q < N) lse[((long long)b * H + h) * N + q] = (m2 + log2f(l)) * 0.69314718055994531f;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+static int make_qkv_tmap(CUtensorMap* tm, const void* qkv, int B, int N, int D3, int box_rows) {
+  const uint64_t dims[3] = {(uint64_t)D3, (uint64_t)N, (uint64_t)B};
+  const uint64_t strides[2] = {(uint64_t)D3 * 2, (uint64_t)N * D3 * 2};
+  const uint32_t box[3] = {64, (uint32_t)box_rows, 1};
+  return make_tmap_bf16(tm, qkv, 3, dims, strides, box);
+}
+
+int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, const tvit_dropout* drop,
+                cudaStream_t s) {
+  if (hd != kHd) return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 attention supports head_dim 64 only (got %d)", hd);
+  const int D = H * hd;
+  if (D % 8 != 0) return fail(TVIT_ERR_BAD_ARG, "attention: embed dim must be a multiple of 8");
+  constexpr int smem_bytes = 5 * kTileBytes + 1024 + 256;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(tc_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  CUtensorMap tm;
+  int rc = make_qkv_tmap(&tm, qkv, B, N, 3 * D, kTile);
+  if (rc != TVIT_OK) return rc;
+  dim3 grid((N + kTile - 1) / kTile, H, B);
+  const float scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
+  tc_attn_fwd_kernel<<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, scale_log2,
+                                                               make_drop(drop));
+  TVIT_LAUNCH_OK();
+  return TVIT_OK;
+}
+
+// backward: see tc_attn_bwd.cu
+
+}  // namespace tvit

@@ -1,9 +1,5 @@
-// placeholder until tc_attn.cu lands (keeps the library linkable)
 #include "common.cuh"
 namespace tvit {
-int tc_attn_fwd(const void*, void*, float*, int, int, int, int, const tvit_dropout*, cudaStream_t) {
-  return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 attention forward not built");
-}
 size_t tc_attn_bwd_workspace(int, int, int, int) { return 0; }
 int tc_attn_bwd(const void*, const void*, const void*, const float*, void*, void*, size_t, int, int, int, int,
                 const tvit_dropout*, cudaStream_t) {
