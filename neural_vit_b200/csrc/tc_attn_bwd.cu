@@ -1,8 +1,389 @@
-#include "common.cuh"
+// Flash-attention backward for sm_100a (head_dim 64, bf16 operands, fp32 accumulate in TMEM).
+//
+// One CTA per (128-key tile j, head, sample) loops over the 128-query tiles i.  Per (i, j):
+//   S  = Q_i K_j^T          tcgen05.mma SS  (A = Q_i  K-major,  B = K_j  K-major)   -> TMEM tS  [128 x 128]
+//   dP = dO_i V_j^T         tcgen05.mma SS  (A = dO_i K-major,  B = V_j  K-major)   -> TMEM tDP [128 x 128]
+//   softmax warps (thread == query row): P = exp2(S*c - lse2), dS = P o (dP o mask - D) * scale,
+//       written as bf16 into two 128B-swizzled smem tiles sP / sDS laid out [q rows][kv contiguous]
+//   dV_j += P^T  dO_i       A = sP  read MN-major (M = kv),  B = dO_i read MN-major (N = hd)  -> TMEM tDV
+//   dK_j += dS^T Q_i        A = sDS read MN-major,           B = Q_i  read MN-major           -> TMEM tDK
+//   dQ_i  = dS   K_j        A = sDS read K-major (M = q),    B = K_j  read MN-major           -> TMEM tDQ
+// The same smem tile serves as a K-major and as an MN-major UMMA operand (the 128B swizzle is a pure
+// address function), so neither P nor dS is ever transposed.  dQ_i partial tiles are drained by four
+// dedicated warps with coalesced 16-byte fp32 reductions into a tile-chunked accumulator and converted
+// to bf16 by a finishing kernel; dK_j / dV_j stay in TMEM across the whole query loop.
+// D = rowsum(dO o O) and lse are read per query row (one scalar each per thread per tile).
+#include "tc_common.cuh"
+
 namespace tvit {
-size_t tc_attn_bwd_workspace(int, int, int, int) { return 0; }
-int tc_attn_bwd(const void*, const void*, const void*, const float*, void*, void*, size_t, int, int, int, int,
-                const tvit_dropout*, cudaStream_t) {
-  return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 attention backward not built");
+
+constexpr int kHdB = 64;
+constexpr int kTileB = 128;
+constexpr int kTileBytesB = kTileB * kHdB * 2;  // 16384: one [128 x 64] bf16 operand tile
+constexpr int kPBytes = kTileB * kTileB * 2;    // 32768: one [128 x 128] bf16 P / dS tile (two 64-wide blocks)
+constexpr int kAttnBwdThreads = 384;
+
+__host__ __device__ __forceinline__ unsigned long long attn_drop_row_base_b(int b, int H, int h, int N, int q) {
+  const unsigned long long npad = (unsigned long long)((N + 7) & ~7);
+  return (((unsigned long long)b * H + h) * N + q) * npad;
 }
+
+struct AttnBwdSmem {
+  uint64_t kv_full, qdo_full[2], qdo_empty[2], s_full, s_free, p_full, mma_done, dq_full, dq_free;
+  uint32_t tmem_base;
+};
+
+// Dvec[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                     float* __restrict__ dvec, int B, int N, int H) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)B * N * H;
+  if (idx >= total) return;
+  const int h = (int)(idx % H);
+  const long long row = idx / H;  // b*N + q
+  const int b = (int)(row / N), q = (int)(row % N);
+  const __nv_bfloat16* po = o + row * (long long)(H * kHdB) + h * kHdB;
+  const __nv_bfloat16* pd = dout + row * (long long)(H * kHdB) + h * kHdB;
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kHdB / 8; ++c) {
+    const uint4 a = *reinterpret_cast<const uint4*>(po + 8 * c);
+    const uint4 d = *reinterpret_cast<const uint4*>(pd + 8 * c);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[t]));
+      const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[t]));
+      s += fa.x * fd.x + fa.y * fd.y;
+    }
+  }
+  dvec[((long long)b * H + h) * N + q] = s;
+}
+
+// dq accumulator layout: [(b*H+h)][q tile][16 chunks][128 rows][4 fp32]
+__global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_bfloat16* __restrict__ dqkv, int B,
+                                          int N, int H, int nq) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * nq * 16 * 128;
+  if (idx >= total) return;
+  const int r = (int)(idx & 127);
+  const int c = (int)((idx >> 7) & 15);
+  const long long t = idx >> 11;  // (b*H+h)*nq + i
+  const int i = (int)(t % nq);
+  const long long bh = t / nq;
+  const int h = (int)(bh % H), b = (int)(bh / H);
+  const int q = i * kTileB + r;
+  if (q >= N) return;
+  const float4 v = *reinterpret_cast<const float4*>(dqacc + idx * 4);
+  uint2 o;
+  o.x = pack_bf16(v.x, v.y);
+  o.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(dqkv + ((long long)b * N + q) * (3LL * H * kHdB) + h * kHdB + 4 * c) = o;
+}
+
+__global__ void __launch_bounds__(kAttnBwdThreads, 1)
+tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const float* __restrict__ lse, const float* __restrict__ dvec, float* __restrict__ dqacc,
+                   __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale, DropCfg drop) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kTileBytesB;
+  uint8_t* sQdO = smem + 2 * kTileBytesB;                 // stage s: Q at +s*32K, dO at +s*32K+16K
+  uint8_t* sP = smem + 2 * kTileBytesB + 4 * kTileBytesB;  // 32K
+  uint8_t* sDS = sP + kPBytes;                             // 32K
+  AttnBwdSmem* sm = reinterpret_cast<AttnBwdSmem*>(sDS + kPBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * kHdB;
+  const int kv0 = jt * kTileB;
+  const int nq = (N + kTileB - 1) / kTileB;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sm->kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm->qdo_full[i], 1);
+      mbar_init(&sm->qdo_empty[i], 1);
+    }
+    mbar_init(&sm->s_full, 1);
+    mbar_init(&sm->s_free, 128);
+    mbar_init(&sm->p_full, 128);
+    mbar_init(&sm->mma_done, 1);
+    mbar_init(&sm->dq_full, 1);
+    mbar_init(&sm->dq_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(&sm->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+
+  if (warp == 4) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+      mbar_expect_tx(&sm->kv_full, 2 * kTileBytesB);
+      tma_load_3d(sK, &tm_qkv, &sm->kv_full, D + h * kHdB, kv0, b);
+      tma_load_3d(sV, &tm_qkv, &sm->kv_full, 2 * D + h * kHdB, kv0, b);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i & 1;
+        mbar_wait(&sm->qdo_empty[st], (((uint32_t)i >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&sm->qdo_full[st], 2 * kTileBytesB);
+        uint8_t* sQ = sQdO + st * 2 * kTileBytesB;
+        tma_load_3d(sQ, &tm_qkv, &sm->qdo_full[st], h * kHdB, i * kTileB, b);
+        tma_load_3d(sQ + kTileBytesB, &tm_do, &sm->qdo_full[st], h * kHdB, i * kTileB, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP: both operands K-major
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);    // dV, dK: A (sP/sDS) MN-major, B MN-major
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);    // dQ: A (sDS) K-major, B (K_j) MN-major
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sDS);
+      mbar_wait(&sm->kv_full, 0);
+      auto issue_sdp = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(&sm->qdo_full[st], ((uint32_t)i >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQdO + st * 2 * kTileBytesB), aDO = aQ + kTileBytesB;
+#pragma unroll
+        for (int k = 0; k < kHdB / 16; ++k)
+          umma_ss(tS, umma_smem_desc(aQ + k * 32, 0, 1024), umma_smem_desc(aK + k * 32, 0, 1024), idesc_s,
+                  k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kHdB / 16; ++k)
+          umma_ss(tDP, umma_smem_desc(aDO + k * 32, 0, 1024), umma_smem_desc(aV + k * 32, 0, 1024), idesc_s,
+                  k > 0 ? 1u : 0u);
+        tc_commit(&sm->s_full);
+      };
+      issue_sdp(0);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i & 1;
+        if (i + 1 < nq) {
+          mbar_wait(&sm->s_free, (uint32_t)i & 1u);  // softmax_i has consumed tS / tDP
+          tc_fence_after();
+          issue_sdp(i + 1);
+        }
+        mbar_wait(&sm->p_full, (uint32_t)i & 1u);  // sP / sDS written for tile i
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQdO + st * 2 * kTileBytesB), aDO = aQ + kTileBytesB;
+        // reduction over the 128 query rows in 8 steps of 16 (2048 B per step in the MN-major tiles)
+#pragma unroll
+        for (int k = 0; k < kTileB / 16; ++k)
+          umma_ss(tDV, umma_smem_desc(aP + k * 2048, 16384, 1024), umma_smem_desc(aDO + k * 2048, 16384, 1024),
+                  idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kTileB / 16; ++k)
+          umma_ss(tDK, umma_smem_desc(aDS + k * 2048, 16384, 1024), umma_smem_desc(aQ + k * 2048, 16384, 1024),
+                  idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+        if (i > 0) {
+          mbar_wait(&sm->dq_free, (uint32_t)(i - 1) & 1u);  // drain warps have read dQ_{i-1}
+          tc_fence_after();
+        }
+        // reduction over the 128 keys: sDS K-major (two 64-key blocks 16 KB apart), K_j MN-major
+#pragma unroll
+        for (int k = 0; k < kTileB / 16; ++k)
+          umma_ss(tDQ, umma_smem_desc(aDS + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024),
+                  umma_smem_desc(aK + k * 2048, 16384, 1024), idesc_q, k > 0 ? 1u : 0u);
+        tc_commit(&sm->qdo_empty[st]);
+        tc_commit(&sm->dq_full);
+        tc_commit(&sm->mma_done);
+      }
+    }
+  } else if (warp < 4) {
+    // ============================ softmax warps (thread == query row) ============================
+    const int r = warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float c_log2 = scale * 1.4426950408889634f;
+    const float* lse_bh = lse + ((long long)b * H + h) * N;
+    const float* dv_bh = dvec + ((long long)b * H + h) * N;
+    for (int i = 0; i < nq; ++i) {
+      const int q = i * kTileB + r;
+      const float lse2 = (q < N) ? lse_bh[q] * 1.4426950408889634f : INFINITY;
+      const float Dq = (q < N) ? dv_bh[q] : 0.f;
+      const unsigned long long rowe = attn_drop_row_base_b(b, H, h, N, q < N ? q : 0) + (unsigned long long)kv0;
+      mbar_wait(&sm->s_full, (uint32_t)i & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dp[32];
+        tmem_ld32(tS + lane_off + c * 32, sv);
+        tmem_ld32(tDP + lane_off + c * 32, dp);
+        tmem_ld_wait();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[4] = {0, 0, 0, 0};
+          if (drop.thr16 != 0) drop_bits8(drop, (rowe >> 3) + (unsigned long long)(c * 4 + g), w);
+#pragma unroll
+          for (int t = 0; t < 8; t += 2) {
+            float p0 = exp2f(__uint_as_float(sv[g * 8 + t]) * c_log2 - lse2);
+            float p1 = exp2f(__uint_as_float(sv[g * 8 + t + 1]) * c_log2 - lse2);
+            float d0 = __uint_as_float(dp[g * 8 + t]), d1 = __uint_as_float(dp[g * 8 + t + 1]);
+            if (drop.thr16 != 0) {
+              const uint32_t b0 = w[t >> 1] & 0xffffu, b1 = w[t >> 1] >> 16;
+              const float m0 = b0 >= drop.thr16 ? drop.inv_keep : 0.f, m1 = b1 >= drop.thr16 ? drop.inv_keep : 0.f;
+              d0 *= m0;
+              d1 *= m1;
+              const float s0 = p0 * (d0 - Dq) * scale, s1 = p1 * (d1 - Dq) * scale;
+              p0 *= m0;
+              p1 *= m1;
+              dk[g * 4 + (t >> 1)] = pack_bf16(s0, s1);
+            } else {
+              dk[g * 4 + (t >> 1)] = pack_bf16(p0 * (d0 - Dq) * scale, p1 * (d1 - Dq) * scale);
+            }
+            pk[g * 4 + (t >> 1)] = pack_bf16(p0, p1);
+          }
+        }
+        if (c == 0 && i > 0) {
+          mbar_wait(&sm->mma_done, (uint32_t)(i - 1) & 1u);  // previous tile's MMAs have finished reading sP / sDS
+        }
+        // row r of block (c >> 1): 16-byte pieces (c & 1) * 4 + g, XOR-swizzled with (r & 7)
+        const uint32_t row_off = (uint32_t)(c >> 1) * 16384u + (uint32_t)r * 128u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t piece = (uint32_t)(((c & 1) * 4 + g) ^ (r & 7)) * 16u;
+          *reinterpret_cast<uint4*>(sP + row_off + piece) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          *reinterpret_cast<uint4*>(sDS + row_off + piece) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sm->s_free);
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&sm->p_full);
+    }
+    // ---- epilogue: dK_j, dV_j from TMEM -> bf16 rows of dqkv ----
+    mbar_wait(&sm->mma_done, (uint32_t)(nq - 1) & 1u);
+    tc_fence_after();
+    const int kv = kv0 + r;
+    __nv_bfloat16* drow = dqkv + ((long long)b * N + kv) * (3LL * D) + h * kHdB;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {  // 0: dK -> cols [D, 2D), 1: dV -> cols [2D, 3D)
+      const uint32_t tsrc = which == 0 ? tDK : tDV;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tsrc + lane_off + c * 32, o);
+        tmem_ld_wait();
+        if (kv < N) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(o[8 * t + 0]), __uint_as_float(o[8 * t + 1]));
+            v.y = pack_bf16(__uint_as_float(o[8 * t + 2]), __uint_as_float(o[8 * t + 3]));
+            v.z = pack_bf16(__uint_as_float(o[8 * t + 4]), __uint_as_float(o[8 * t + 5]));
+            v.w = pack_bf16(__uint_as_float(o[8 * t + 6]), __uint_as_float(o[8 * t + 7]));
+            *reinterpret_cast<uint4*>(drow + (which + 1) * D + c * 32 + 8 * t) = v;
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ============================ dQ drain warps ============================
+    const int qd = warp - 8;  // TMEM lane quarter (warp % 4)
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    float* acc_bh = dqacc + ((long long)b * H + h) * nq * (16LL * 128 * 4);
+    for (int i = 0; i < nq; ++i) {
+      mbar_wait(&sm->dq_full, (uint32_t)i & 1u);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tDQ + lane_off, o0);
+      tmem_ld32(tDQ + lane_off + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sm->dq_free);
+      float* tile = acc_bh + (long long)i * (16 * 128 * 4) + r * 4;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        atomicAdd(reinterpret_cast<float4*>(tile + c * 512),
+                  make_float4(__uint_as_float(o0[4 * c]), __uint_as_float(o0[4 * c + 1]), __uint_as_float(o0[4 * c + 2]),
+                              __uint_as_float(o0[4 * c + 3])));
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        atomicAdd(reinterpret_cast<float4*>(tile + (8 + c) * 512),
+                  make_float4(__uint_as_float(o1[4 * c]), __uint_as_float(o1[4 * c + 1]), __uint_as_float(o1[4 * c + 2]),
+                              __uint_as_float(o1[4 * c + 3])));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static int make_tok_tmap(CUtensorMap* tm, const void* base, int B, int N, int cols) {
+  const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)N, (uint64_t)B};
+  const uint64_t strides[2] = {(uint64_t)cols * 2, (uint64_t)N * cols * 2};
+  const uint32_t box[3] = {64, (uint32_t)kTileB, 1};
+  return make_tmap_bf16(tm, base, 3, dims, strides, box);
+}
+
+// workspace: Dvec [B,H,N] fp32 | dQ accumulator [B*H][nq][16][128][4] fp32
+static size_t ws_dvec_bytes(int B, int N, int H) { return (((size_t)B * H * N * 4) + 255) & ~(size_t)255; }
+
+size_t tc_attn_bwd_workspace(int B, int N, int H, int hd) {
+  (void)hd;
+  const size_t nq = (N + kTileB - 1) / kTileB;
+  return ws_dvec_bytes(B, N, H) + (size_t)B * H * nq * 16 * 128 * 4 * sizeof(float);
+}
+
+int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* ws,
+                size_t ws_bytes, int B, int N, int H, int hd, const tvit_dropout* drop, cudaStream_t s) {
+  if (hd != kHdB) return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 attention supports head_dim 64 only (got %d)", hd);
+  if (!ws || ws_bytes < tc_attn_bwd_workspace(B, N, H, hd))
+    return fail(TVIT_ERR_BAD_ARG, "attn_bwd: workspace too small (%zu < %zu)", ws_bytes,
+                tc_attn_bwd_workspace(B, N, H, hd));
+  const int D = H * hd;
+  const int nq = (N + kTileB - 1) / kTileB;
+  float* dvec = reinterpret_cast<float*>(ws);
+  float* dqacc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + ws_dvec_bytes(B, N, H));
+  const size_t dq_bytes = (size_t)B * H * nq * 16 * 128 * 4 * sizeof(float);
+
+  constexpr int smem_bytes = 2 * kTileBytesB + 4 * kTileBytesB + 2 * kPBytes + 1024 + 256;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(tc_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+
+  TVIT_CUDA_OK(cudaMemsetAsync(dqacc, 0, dq_bytes, s));
+  {
+    const long long total = (long long)B * N * H;
+    attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, dvec, B, N, H);
+    TVIT_LAUNCH_OK();
+  }
+  CUtensorMap tm_qkv, tm_do;
+  int rc;
+  if ((rc = make_tok_tmap(&tm_qkv, qkv, B, N, 3 * D)) != TVIT_OK) return rc;
+  if ((rc = make_tok_tmap(&tm_do, dout, B, N, D)) != TVIT_OK) return rc;
+  dim3 grid(nq, H, B);
+  const float scale = 1.0f / sqrtf((float)hd);
+  tc_attn_bwd_kernel<<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, lse, dvec, dqacc,
+                                                               (__nv_bfloat16*)dqkv, N, H, scale, make_drop(drop));
+  TVIT_LAUNCH_OK();
+  {
+    const long long total = (long long)B * H * nq * 16 * 128;
+    attn_bwd_dq_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dqacc, (__nv_bfloat16*)dqkv, B, N, H, nq);
+    TVIT_LAUNCH_OK();
+  }
+  return TVIT_OK;
+}
+
 }  // namespace tvit
