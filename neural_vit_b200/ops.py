@@ -15,6 +15,38 @@ from . import _lib as L
 
 DropSpec = Optional[Tuple[int, int, float]]  # (seed, site, p)
 
+# --- instrumentation used by bench.py (off by default) -------------------------------------------------
+# LAUNCHES counts the CUDA kernels this library launched (per C call: see _KERNELS_PER_CALL);
+# when TIMED is a dict {name: [(start_event, end_event), ...]} the named ops are bracketed by CUDA events
+# on the launching stream so a kernel's duration can be measured inside a timed training step.
+LAUNCHES = {"count": 0}
+TIMED = None
+_KERNELS_PER_CALL = {"gemm": 1, "attn_fwd": 1, "attn_bwd": 3, "attn_bwd_simt": 2, "attn_probs": 1, "im2col": 1,
+                     "ln_fwd": 1, "ln_bwd": 1, "branch_grad_prep": 1, "colsum": 1, "cast_weight": 1,
+                     "ls_finalize": 1, "cls_rows": 1, "embed_bwd_prep": 1, "pos_grad_reduce": 1, "adamw": 1}
+
+
+def _count(name: str) -> None:
+    LAUNCHES["count"] += _KERNELS_PER_CALL[name]
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+        self.on = TIMED is not None and name in TIMED
+
+    def __enter__(self):
+        if self.on:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e.record()
+            TIMED[self.name].append((self.s, self.e))
+        return False
+
 _TORCH_DTYPE = {L.F32: torch.float32, L.BF16: torch.bfloat16}
 
 
@@ -79,41 +111,51 @@ def gemm(engine: int, dtype: int, a: torch.Tensor, b: torch.Tensor, M: int, N: i
         args.pos_k, args.pos_f, args.pos_t = (p.data_ptr() for p in pos)
         args.Kp, args.Fp, args.Tp = grid3
     args.split_k = split_k
-    L.check(L.load().tvit_gemm(ctypes.byref(args), _stream()), "tvit_gemm")
+    _count("gemm")
+    with _timed("gemm_e%d%s" % (epilogue, "_tn" if trans_a else "")):
+        L.check(L.load().tvit_gemm(ctypes.byref(args), _stream()), "tvit_gemm")
 
 
 def attn_fwd(engine, dtype, qkv, out, lse, B, N, H, hd, drop: DropSpec = None) -> None:
-    L.check(L.load().tvit_attn_fwd(engine, dtype, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, hd,
-                                   _drop_ptr(drop), _stream()), "tvit_attn_fwd")
+    _count("attn_fwd")
+    with _timed("attn_fwd"):
+        L.check(L.load().tvit_attn_fwd(engine, dtype, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, hd,
+                                       _drop_ptr(drop), _stream()), "tvit_attn_fwd")
 
 
 def attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, B, N, H, hd, drop: DropSpec = None) -> None:
     lib = L.load()
     nbytes = int(lib.tvit_attn_bwd_workspace_bytes(engine, dtype, B, N, H, hd))
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qkv.device)
-    L.check(lib.tvit_attn_bwd(engine, dtype, qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-                              dqkv.data_ptr(), ws.data_ptr(), nbytes, B, N, H, hd, _drop_ptr(drop), _stream()),
-            "tvit_attn_bwd")
+    _count("attn_bwd" if engine == L.ENGINE_TCGEN05 else "attn_bwd_simt")
+    with _timed("attn_bwd"):
+        L.check(lib.tvit_attn_bwd(engine, dtype, qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                  dqkv.data_ptr(), ws.data_ptr(), nbytes, B, N, H, hd, _drop_ptr(drop), _stream()),
+                "tvit_attn_bwd")
 
 
 def attn_probs(dtype, qkv, probs, B, N, H, hd) -> None:
+    _count("attn_probs")
     L.check(L.load().tvit_attn_probs(dtype, qkv.data_ptr(), probs.data_ptr(), B, N, H, hd, _stream()),
             "tvit_attn_probs")
 
 
 def im2col(x, cols, dtype, B, K, F, T, pk, pf, pt) -> None:
     _req(x, torch.float32, "im2col x")
+    _count("im2col")
     L.check(L.load().tvit_im2col(x.data_ptr(), cols.data_ptr(), dtype, B, K, F, T, pk, pf, pt, _stream()),
             "tvit_im2col")
 
 
 def ln_fwd(x, x_row_stride, weight, bias, y, dtype, mean, rstd, rows, D, eps=1e-5) -> None:
+    _count("ln_fwd")
     L.check(L.load().tvit_ln_fwd(x.data_ptr(), x_row_stride, weight.data_ptr(), bias.data_ptr(), y.data_ptr(), dtype,
                                  _ptr(mean), _ptr(rstd), rows, D, eps, _stream()), "tvit_ln_fwd")
 
 
 def ln_bwd(dy, dtype, x, x_row_stride, mean, rstd, weight, g_res, dx, dx_row_stride, dweight, dbias, rows, D, *,
            gp=None, row_scale=None, rows_per_group=0, drop: DropSpec = None, gp_colsum=None) -> None:
+    _count("ln_bwd")
     L.check(L.load().tvit_ln_bwd(dy.data_ptr(), dtype, x.data_ptr(), x_row_stride, mean.data_ptr(), rstd.data_ptr(),
                                  weight.data_ptr(), _ptr(g_res), dx.data_ptr(), dx_row_stride, _ptr(dweight),
                                  _ptr(dbias), _ptr(gp), _ptr(row_scale), rows_per_group, _drop_ptr(drop),
@@ -121,39 +163,47 @@ def ln_bwd(dy, dtype, x, x_row_stride, mean, rstd, weight, g_res, dx, dx_row_str
 
 
 def branch_grad_prep(g, rows, D, row_scale, rows_per_group, drop: DropSpec, gp, dtype, colsum) -> None:
+    _count("branch_grad_prep")
     L.check(L.load().tvit_branch_grad_prep(g.data_ptr(), rows, D, _ptr(row_scale), rows_per_group, _drop_ptr(drop),
                                            gp.data_ptr(), dtype, _ptr(colsum), _stream()), "tvit_branch_grad_prep")
 
 
 def colsum(x, dtype, rows, C, ld, out) -> None:
+    _count("colsum")
     L.check(L.load().tvit_colsum(x.data_ptr(), dtype, rows, C, ld, out.data_ptr(), _stream()), "tvit_colsum")
 
 
 def cast_weight(w, R, C, row_scale, out, out_t, dtype) -> None:
+    _count("cast_weight")
     L.check(L.load().tvit_cast_weight(w.data_ptr(), R, C, _ptr(row_scale), _ptr(out), _ptr(out_t), dtype, _stream()),
             "tvit_cast_weight")
 
 
 def ls_finalize(G, W, gamma, bias, cs, dW, dgamma, dbias, R, C) -> None:
+    _count("ls_finalize")
     L.check(L.load().tvit_ls_finalize(G.data_ptr(), _ptr(W), _ptr(gamma), _ptr(bias), cs.data_ptr(), dW.data_ptr(),
                                       _ptr(dgamma), _ptr(dbias), R, C, _stream()), "tvit_ls_finalize")
 
 
 def cls_rows(cls, h, B, N, D, drop: DropSpec) -> None:
+    _count("cls_rows")
     L.check(L.load().tvit_cls_rows(cls.data_ptr(), h.data_ptr(), B, N, D, _drop_ptr(drop), _stream()),
             "tvit_cls_rows")
 
 
 def embed_bwd_prep(g0, B, n, D, drop: DropSpec, gtok, dtype, R, dcls) -> None:
+    _count("embed_bwd_prep")
     L.check(L.load().tvit_embed_bwd_prep(g0.data_ptr(), B, n, D, _drop_ptr(drop), gtok.data_ptr(), dtype,
                                          R.data_ptr(), dcls.data_ptr(), _stream()), "tvit_embed_bwd_prep")
 
 
 def pos_grad_reduce(R, Kp, Fp, Tp, D, dpk, dpf, dpt, dbias) -> None:
+    _count("pos_grad_reduce")
     L.check(L.load().tvit_pos_grad_reduce(R.data_ptr(), Kp, Fp, Tp, D, dpk.data_ptr(), dpf.data_ptr(),
                                           dpt.data_ptr(), dbias.data_ptr(), _stream()), "tvit_pos_grad_reduce")
 
 
 def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> None:
+    _count("adamw")
     L.check(L.load().tvit_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
                                 eps, weight_decay, step, grad_scale, _stream()), "tvit_adamw")

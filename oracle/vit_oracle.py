@@ -255,6 +255,36 @@ def loss_and_grads(x: Tensor, labels: Tensor, p: Dict[str, Tensor], cfg: OracleC
     return logits.detach(), loss.detach(), grads
 
 
+def draw_masks(cfg: OracleConfig, batch: int, generator: Optional[torch.Generator] = None,
+               device="cpu") -> Dict[str, Tensor]:
+    """Draw the keep-masks one train-mode step of the reference consumes (nn.Dropout at model.py:102,104,
+    138,140,224,250 and DropPath at :64-71).  Used by the CPU baseline so that its timed region contains
+    the same O(B*H*N*N) Bernoulli work the reference's train mode does."""
+    N, D, H = cfg.n_patches + 1, cfg.embed_dim, cfg.n_heads
+    hid = int(D * cfg.mlp_ratio)
+
+    def bern(shape, p):
+        return (torch.rand(shape, generator=generator, device=device) >= p).to(torch.float32)
+
+    m: Dict[str, Tensor] = {}
+    if cfg.dropout > 0:
+        m["pos_drop"] = bern((batch, N, D), cfg.dropout)
+        m["head_drop"] = bern((batch, D), cfg.dropout)
+    rates = drop_path_rates(cfg)
+    for i in range(cfg.n_layers):
+        pre = f"blocks.{i}."
+        if cfg.attention_dropout > 0:
+            m[pre + "attn_drop"] = bern((batch, H, N, N), cfg.attention_dropout)
+        if cfg.dropout > 0:
+            m[pre + "proj_drop"] = bern((batch, N, D), cfg.dropout)
+            m[pre + "drop1"] = bern((batch, N, hid), cfg.dropout)
+            m[pre + "drop2"] = bern((batch, N, D), cfg.dropout)
+        if rates[i] > 0:
+            m[pre + "drop_path1"] = bern((batch,), rates[i])
+            m[pre + "drop_path2"] = bern((batch,), rates[i])
+    return m
+
+
 def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
     """state_dict layout of the reference, in registration order."""
     D = cfg.embed_dim

@@ -117,9 +117,9 @@ def test_train_mode_dropout_statistics(precision):
     l1, _, g1 = _step(m, x, y)
     torch.manual_seed(5)
     l2, _, g2 = _step(m, x, y)
-    assert abs(float(l1) - float(l2)) < 1e-5
+    assert rel_err(l1, l2) < 1e-5            # same seed -> same masks (fp32 atomics may reorder sums)
     l3, _, _ = _step(m, x, y)
-    assert not torch.equal(l1, l3)
+    assert rel_err(l3, l1) > 1e-4            # a different draw changes the logits
     for k, v in g1.items():
         assert torch.isfinite(v).all(), k
         assert rel_err(v, g2[k]) < 1e-5, k      # same masks; fp32 atomics reorder sums
