@@ -81,7 +81,7 @@ __device__ __forceinline__ void epi_apply1(const EpiParams& p, int m, int n, flo
   } else if (EPI == TVIT_EPI_BIAS_GELU) {
     if (p.bias) v += p.bias[n];
     Act<T>::st((T*)p.aux + m * p.ldaux + n, v);
-    Act<T>::st((T*)p.out + m * p.ldo + n, gelu_f(v) * drop_mult(p.drop, (unsigned long long)m * p.N + n));
+    Act<T>::st((T*)p.out + m * p.ldo + n, gelu_t<T>(v) * drop_mult(p.drop, (unsigned long long)m * p.N + n));
   } else if (EPI == TVIT_EPI_RESIDUAL) {
     if (p.bias) v += p.bias[n];
     v *= drop_mult(p.drop, (unsigned long long)m * p.N + n);
@@ -90,7 +90,7 @@ __device__ __forceinline__ void epi_apply1(const EpiParams& p, int m, int n, flo
     ((float*)p.out)[m * p.ldo + n] = p.resid[m * p.ldres + n] + v;
   } else if (EPI == TVIT_EPI_GELU_BWD) {
     const float h = Act<T>::ld((const T*)p.aux + m * p.ldaux + n);
-    Act<T>::st((T*)p.out + m * p.ldo + n, v * drop_mult(p.drop, (unsigned long long)m * p.N + n) * gelu_grad_f(h));
+    Act<T>::st((T*)p.out + m * p.ldo + n, v * drop_mult(p.drop, (unsigned long long)m * p.N + n) * gelu_grad_t<T>(h));
   } else if (EPI == TVIT_EPI_ACCUM_F32) {
     atomicAdd((float*)p.out + m * p.ldo + n, v);
   } else if (EPI == TVIT_EPI_PATCH_EMBED) {
@@ -130,7 +130,7 @@ __device__ __forceinline__ void epi_apply4(const EpiParams& p, int m, int n0, fl
     float mlt[4];
     drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, mlt);
     st4((T*)p.out + m * p.ldo + n0,
-        make_float4(gelu_f(v.x) * mlt[0], gelu_f(v.y) * mlt[1], gelu_f(v.z) * mlt[2], gelu_f(v.w) * mlt[3]));
+        make_float4(gelu_t<T>(v.x) * mlt[0], gelu_t<T>(v.y) * mlt[1], gelu_t<T>(v.z) * mlt[2], gelu_t<T>(v.w) * mlt[3]));
   } else if (EPI == TVIT_EPI_RESIDUAL) {
     if (p.bias) {
       const float4 b = ld4(p.bias + n0);
@@ -149,8 +149,8 @@ __device__ __forceinline__ void epi_apply4(const EpiParams& p, int m, int n0, fl
     float mlt[4];
     drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, mlt);
     st4((T*)p.out + m * p.ldo + n0,
-        make_float4(v.x * mlt[0] * gelu_grad_f(h.x), v.y * mlt[1] * gelu_grad_f(h.y), v.z * mlt[2] * gelu_grad_f(h.z),
-                    v.w * mlt[3] * gelu_grad_f(h.w)));
+        make_float4(v.x * mlt[0] * gelu_grad_t<T>(h.x), v.y * mlt[1] * gelu_grad_t<T>(h.y), v.z * mlt[2] * gelu_grad_t<T>(h.z),
+                    v.w * mlt[3] * gelu_grad_t<T>(h.w)));
   } else if (EPI == TVIT_EPI_ACCUM_F32) {
     float* o = (float*)p.out + m * p.ldo + n0;
     atomicAdd(o + 0, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
@@ -201,15 +201,15 @@ __device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, co
       uint4 h = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
       *reinterpret_cast<uint4*>((__nv_bfloat16*)p.aux + m * p.ldaux + n0) = h;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = gelu_f(x[j]) * ml[j];
+      for (int j = 0; j < 8; ++j) x[j] = gelu_t<T>(x[j]) * ml[j];
     } else {  // GELU_BWD
       const uint4 h = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.aux + m * p.ldaux + n0);
       const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
-        x[2 * j] = x[2 * j] * ml[2 * j] * gelu_grad_f(f.x);
-        x[2 * j + 1] = x[2 * j + 1] * ml[2 * j + 1] * gelu_grad_f(f.y);
+        x[2 * j] = x[2 * j] * ml[2 * j] * gelu_grad_t<T>(f.x);
+        x[2 * j + 1] = x[2 * j + 1] * ml[2 * j + 1] * gelu_grad_t<T>(f.y);
       }
     }
     uint4 o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));

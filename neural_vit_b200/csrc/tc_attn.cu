@@ -135,25 +135,38 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
       tc_fence_before();
       mbar_arrive(&sm->s_free);
 
-      const int valid = N - j * kTile;  // keys beyond N are masked
-      float mx = -INFINITY;
+      const int valid = N - j * kTile;  // keys beyond N are masked (last tile only)
+      if (valid < kTile) {
 #pragma unroll
-      for (int c = 0; c < 128; ++c) {
-        float v = __uint_as_float(sreg[c]) * scale_log2;
-        v = (c < valid) ? v : -INFINITY;
-        sreg[c] = __float_as_uint(v);
-        mx = fmaxf(mx, v);
+        for (int c = 0; c < 128; ++c)
+          if (c >= valid) sreg[c] = 0xff800000u;  // -inf
       }
-      const float m_new = fmaxf(m2, mx);
-      const float corr = exp2f(m2 - m_new);
-      float rs = 0.f;
+      // ~4.5 instructions per element: FMNMX, FFMA, MUFU.EX2, FADD, half a CVT
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 128; ++c) {
-        const float p = exp2f(__uint_as_float(sreg[c]) - m_new);
-        rs += p;
-        sreg[c] = __float_as_uint(p);
+      for (int c = 0; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sreg[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(sreg[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sreg[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sreg[c + 3]));
       }
-      l = l * corr + rs;
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const float m_new = fmaxf(m2, mx * scale_log2);  // running max in the scaled log2 domain
+      const float corr = ex2_approx(m2 - m_new);
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[c]), scale_log2, -m_new));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[c + 1]), scale_log2, -m_new));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[c + 2]), scale_log2, -m_new));
+        const float p3 = ex2_approx(fmaf(__uint_as_float(sreg[c + 3]), scale_log2, -m_new));
+        rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+        sreg[c] = __float_as_uint(p0);
+        sreg[c + 1] = __float_as_uint(p1);
+        sreg[c + 2] = __float_as_uint(p2);
+        sreg[c + 3] = __float_as_uint(p3);
+      }
+      l = l * corr + ((rs0 + rs1) + (rs2 + rs3));
       if (drop.thr16 != 0) {
         const unsigned long long g0 = (rowe + (unsigned long long)j * kTile) >> 3;
 #pragma unroll

@@ -13,6 +13,8 @@
 // dedicated warps with coalesced 16-byte fp32 reductions into a tile-chunked accumulator and converted
 // to bf16 by a finishing kernel; dK_j / dV_j stay in TMEM across the whole query loop.
 // D = rowsum(dO o O) and lse are read per query row (one scalar each per thread per tile).
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace tvit {
@@ -21,7 +23,7 @@ constexpr int kHdB = 64;
 constexpr int kTileB = 128;
 constexpr int kTileBytesB = kTileB * kHdB * 2;  // 16384: one [128 x 64] bf16 operand tile
 constexpr int kPBytes = kTileB * kTileB * 2;    // 32768: one [128 x 128] bf16 P / dS tile (two 64-wide blocks)
-constexpr int kAttnBwdThreads = 384;
+constexpr int kAttnBwdThreads = 512;  // warps 0-7 softmax, 8 TMA, 9 MMA, 12-15 dQ drain
 
 __host__ __device__ __forceinline__ unsigned long long attn_drop_row_base_b(int b, int H, int h, int N, int q) {
   const unsigned long long npad = (unsigned long long)((N + 7) & ~7);
@@ -29,7 +31,7 @@ __host__ __device__ __forceinline__ unsigned long long attn_drop_row_base_b(int 
 }
 
 struct AttnBwdSmem {
-  uint64_t kv_full, qdo_full[2], qdo_empty[2], s_full, s_free, p_full, mma_done, dq_full, dq_free;
+  uint64_t kv_full, qdo_full[2], qdo_empty[2], s_full, s_free, p_full, mma_done[2], dq_full, dq_free;
   uint32_t tmem_base;
 };
 
@@ -81,6 +83,7 @@ __global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_
   *reinterpret_cast<uint2*>(dqkv + ((long long)b * N + q) * (3LL * H * kHdB) + h * kHdB + 4 * c) = o;
 }
 
+template <bool kDrop>
 __global__ void __launch_bounds__(kAttnBwdThreads, 1)
 tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const float* __restrict__ lse, const float* __restrict__ dvec, float* __restrict__ dqacc,
@@ -90,11 +93,11 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sK = smem;
   uint8_t* sV = smem + kTileBytesB;
   uint8_t* sQdO = smem + 2 * kTileBytesB;                 // stage s: Q at +s*32K, dO at +s*32K+16K
-  uint8_t* sP = smem + 2 * kTileBytesB + 4 * kTileBytesB;  // 32K
-  uint8_t* sDS = sP + kPBytes;                             // 32K
-  AttnBwdSmem* sm = reinterpret_cast<AttnBwdSmem*>(sDS + kPBytes);
+  uint8_t* sPDS = smem + 6 * kTileBytesB;  // buffer u (= tile parity): P at +u*64K, dS at +u*64K+32K
+  AttnBwdSmem* sm = reinterpret_cast<AttnBwdSmem*>(sPDS + 4 * kPBytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int D = H * kHdB;
   const int kv0 = jt * kTileB;
@@ -107,14 +110,15 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_init(&sm->qdo_empty[i], 1);
     }
     mbar_init(&sm->s_full, 1);
-    mbar_init(&sm->s_free, 128);
-    mbar_init(&sm->p_full, 128);
-    mbar_init(&sm->mma_done, 1);
+    mbar_init(&sm->s_free, 8);   // one elected arrive per softmax warp
+    mbar_init(&sm->p_full, 8);
+    mbar_init(&sm->mma_done[0], 1);
+    mbar_init(&sm->mma_done[1], 1);
     mbar_init(&sm->dq_full, 1);
     mbar_init(&sm->dq_free, 128);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(&sm->tmem_base, 512);
     tmem_relinquish();
   }
@@ -124,96 +128,119 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tmem = sm->tmem_base;
   const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
 
-  if (warp == 4) {
+  // Role code below is warp-uniform (all 32 lanes run the loops and the barrier waits); only the TMA / MMA /
+  // commit instructions themselves are predicated on one elected lane.  Issuing them from divergent code
+  // (`if (lane == 0)`) makes ptxas wrap every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST loop (~100 clk each).
+  if (warp == 8) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tm_qkv);
       tma_prefetch_desc(&tm_do);
       mbar_expect_tx(&sm->kv_full, 2 * kTileBytesB);
       tma_load_3d(sK, &tm_qkv, &sm->kv_full, D + h * kHdB, kv0, b);
       tma_load_3d(sV, &tm_qkv, &sm->kv_full, 2 * D + h * kHdB, kv0, b);
-      for (int i = 0; i < nq; ++i) {
-        const int st = i & 1;
-        mbar_wait(&sm->qdo_empty[st], (((uint32_t)i >> 1) & 1u) ^ 1u);
+    }
+    __syncwarp();
+    for (int i = 0; i < nq; ++i) {
+      const int st = i & 1;
+      mbar_wait_backoff(&sm->qdo_empty[st], (((uint32_t)i >> 1) & 1u) ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(&sm->qdo_full[st], 2 * kTileBytesB);
         uint8_t* sQ = sQdO + st * 2 * kTileBytesB;
         tma_load_3d(sQ, &tm_qkv, &sm->qdo_full[st], h * kHdB, i * kTileB, b);
         tma_load_3d(sQ + kTileBytesB, &tm_do, &sm->qdo_full[st], h * kHdB, i * kTileB, b);
       }
+      __syncwarp();
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP: both operands K-major
-      constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);    // dV, dK: A (sP/sDS) MN-major, B MN-major
-      constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);    // dQ: A (sDS) K-major, B (K_j) MN-major
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sDS);
-      mbar_wait(&sm->kv_full, 0);
-      auto issue_sdp = [&](int i) {
-        const int st = i & 1;
-        mbar_wait(&sm->qdo_full[st], ((uint32_t)i >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t aQ = smem_u32(sQdO + st * 2 * kTileBytesB), aDO = aQ + kTileBytesB;
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP: both operands K-major
+    constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);    // dV, dK: A (sP/sDS) MN-major, B MN-major
+    constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);    // dQ: A (sDS) K-major, B (K_j) MN-major
+    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+    mbar_wait(&sm->kv_full, 0);
+    auto issue_sdp = [&](int i) {
+      const int st = i & 1;
+      mbar_wait(&sm->qdo_full[st], ((uint32_t)i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQdO + st * 2 * kTileBytesB), aDO = aQ + kTileBytesB;
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kHdB / 16; ++k)
-          umma_ss(tS, umma_smem_desc(aQ + k * 32, 0, 1024), umma_smem_desc(aK + k * 32, 0, 1024), idesc_s,
-                  k > 0 ? 1u : 0u);
+          for (int k = 0; k < kHdB / 16; ++k)
+            umma_ss(tS, umma_smem_desc(aQ + k * 32, 0, 1024), umma_smem_desc(aK + k * 32, 0, 1024), idesc_s,
+                    k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < kHdB / 16; ++k)
-          umma_ss(tDP, umma_smem_desc(aDO + k * 32, 0, 1024), umma_smem_desc(aV + k * 32, 0, 1024), idesc_s,
-                  k > 0 ? 1u : 0u);
+          for (int k = 0; k < kHdB / 16; ++k)
+            umma_ss(tDP, umma_smem_desc(aDO + k * 32, 0, 1024), umma_smem_desc(aV + k * 32, 0, 1024), idesc_s,
+                    k > 0 ? 1u : 0u);
         tc_commit(&sm->s_full);
-      };
-      issue_sdp(0);
-      for (int i = 0; i < nq; ++i) {
-        const int st = i & 1;
-        if (i + 1 < nq) {
-          mbar_wait(&sm->s_free, (uint32_t)i & 1u);  // softmax_i has consumed tS / tDP
-          tc_fence_after();
-          issue_sdp(i + 1);
-        }
-        mbar_wait(&sm->p_full, (uint32_t)i & 1u);  // sP / sDS written for tile i
+      }
+      __syncwarp();
+    };
+    issue_sdp(0);
+    for (int i = 0; i < nq; ++i) {
+      const int st = i & 1;
+      if (i + 1 < nq) {
+        mbar_wait(&sm->s_free, (uint32_t)i & 1u);  // softmax_i has consumed tS / tDP
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sQdO + st * 2 * kTileBytesB), aDO = aQ + kTileBytesB;
-        // reduction over the 128 query rows in 8 steps of 16 (2048 B per step in the MN-major tiles)
+        issue_sdp(i + 1);
+      }
+      mbar_wait(&sm->p_full, (uint32_t)i & 1u);  // sP / sDS written for tile i
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQdO + st * 2 * kTileBytesB), aDO = aQ + kTileBytesB;
+      const uint32_t aP = smem_u32(sPDS + st * 2 * kPBytes), aDS = aP + kPBytes;
+      if (elect_one()) {
+          // reduction over the 128 query rows in 8 steps of 16 (2048 B per step in the MN-major tiles)
 #pragma unroll
-        for (int k = 0; k < kTileB / 16; ++k)
-          umma_ss(tDV, umma_smem_desc(aP + k * 2048, 16384, 1024), umma_smem_desc(aDO + k * 2048, 16384, 1024),
-                  idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kTileB / 16; ++k)
+            umma_ss(tDV, umma_smem_desc(aP + k * 2048, 16384, 1024), umma_smem_desc(aDO + k * 2048, 16384, 1024),
+                    idesc_t, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < kTileB / 16; ++k)
-          umma_ss(tDK, umma_smem_desc(aDS + k * 2048, 16384, 1024), umma_smem_desc(aQ + k * 2048, 16384, 1024),
-                  idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-        if (i > 0) {
-          mbar_wait(&sm->dq_free, (uint32_t)(i - 1) & 1u);  // drain warps have read dQ_{i-1}
-          tc_fence_after();
-        }
+          for (int k = 0; k < kTileB / 16; ++k)
+            umma_ss(tDK, umma_smem_desc(aDS + k * 2048, 16384, 1024), umma_smem_desc(aQ + k * 2048, 16384, 1024),
+                    idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+      }
+      __syncwarp();
+      if (i > 0) {
+        mbar_wait(&sm->dq_free, (uint32_t)(i - 1) & 1u);  // drain warps have read dQ_{i-1}
+        tc_fence_after();
+      }
+      if (elect_one()) {
         // reduction over the 128 keys: sDS K-major (two 64-key blocks 16 KB apart), K_j MN-major
 #pragma unroll
-        for (int k = 0; k < kTileB / 16; ++k)
-          umma_ss(tDQ, umma_smem_desc(aDS + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024),
-                  umma_smem_desc(aK + k * 2048, 16384, 1024), idesc_q, k > 0 ? 1u : 0u);
+          for (int k = 0; k < kTileB / 16; ++k)
+            umma_ss(tDQ, umma_smem_desc(aDS + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024),
+                    umma_smem_desc(aK + k * 2048, 16384, 1024), idesc_q, k > 0 ? 1u : 0u);
         tc_commit(&sm->qdo_empty[st]);
         tc_commit(&sm->dq_full);
-        tc_commit(&sm->mma_done);
+        tc_commit(&sm->mma_done[st]);
       }
+      __syncwarp();
     }
-  } else if (warp < 4) {
-    // ============================ softmax warps (thread == query row) ============================
-    const int r = warp * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  } else if (warp < 8) {
+    // ============ softmax warps: thread == query row (TMEM lane quarter warp % 4), key half warp / 4 ============
+    const int qd4 = warp & 3, half = warp >> 2;
+    const int r = qd4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd4 * 32) << 16;
     const float c_log2 = scale * 1.4426950408889634f;
     const float* lse_bh = lse + ((long long)b * H + h) * N;
     const float* dv_bh = dvec + ((long long)b * H + h) * N;
+    float lse_next = (r < N) ? lse_bh[r] : INFINITY, d_next = (r < N) ? dv_bh[r] : 0.f;
     for (int i = 0; i < nq; ++i) {
       const int q = i * kTileB + r;
-      const float lse2 = (q < N) ? lse_bh[q] * 1.4426950408889634f : INFINITY;
-      const float Dq = (q < N) ? dv_bh[q] : 0.f;
+      const float lse2 = lse_next * 1.4426950408889634f;  // +inf for rows past N -> P = 0
+      const float Dq = d_next * scale;  // dS = P * (dP * scale - D * scale)
+      {  // prefetch the next tile's row statistics so the global-load latency is off the critical path
+        const int qn = q + kTileB;
+        lse_next = (qn < N) ? lse_bh[qn] : INFINITY;
+        d_next = (qn < N) ? dv_bh[qn] : 0.f;
+      }
+      const uint32_t aPbuf = smem_u32(sPDS) + (uint32_t)(i & 1) * 2u * kPBytes;  // P buffer; dS follows at +32K
       const unsigned long long rowe = attn_drop_row_base_b(b, H, h, N, q < N ? q : 0) + (unsigned long long)kv0;
       mbar_wait(&sm->s_full, (uint32_t)i & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * half; c < 2 * half + 2; ++c) {
         uint32_t sv[32], dp[32];
         tmem_ld32(tS + lane_off + c * 32, sv);
         tmem_ld32(tDP + lane_off + c * 32, dp);
@@ -222,51 +249,54 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t w[4] = {0, 0, 0, 0};
-          if (drop.thr16 != 0) drop_bits8(drop, (rowe >> 3) + (unsigned long long)(c * 4 + g), w);
+          if (kDrop) drop_bits8(drop, (rowe >> 3) + (unsigned long long)(c * 4 + g), w);
 #pragma unroll
           for (int t = 0; t < 8; t += 2) {
-            float p0 = exp2f(__uint_as_float(sv[g * 8 + t]) * c_log2 - lse2);
-            float p1 = exp2f(__uint_as_float(sv[g * 8 + t + 1]) * c_log2 - lse2);
+            float p0 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_log2, -lse2));
+            float p1 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t + 1]), c_log2, -lse2));
             float d0 = __uint_as_float(dp[g * 8 + t]), d1 = __uint_as_float(dp[g * 8 + t + 1]);
-            if (drop.thr16 != 0) {
+            if (kDrop) {
               const uint32_t b0 = w[t >> 1] & 0xffffu, b1 = w[t >> 1] >> 16;
               const float m0 = b0 >= drop.thr16 ? drop.inv_keep : 0.f, m1 = b1 >= drop.thr16 ? drop.inv_keep : 0.f;
               d0 *= m0;
               d1 *= m1;
-              const float s0 = p0 * (d0 - Dq) * scale, s1 = p1 * (d1 - Dq) * scale;
+              const float s0 = p0 * fmaf(d0, scale, -Dq), s1 = p1 * fmaf(d1, scale, -Dq);
               p0 *= m0;
               p1 *= m1;
               dk[g * 4 + (t >> 1)] = pack_bf16(s0, s1);
             } else {
-              dk[g * 4 + (t >> 1)] = pack_bf16(p0 * (d0 - Dq) * scale, p1 * (d1 - Dq) * scale);
+              dk[g * 4 + (t >> 1)] = pack_bf16(p0 * fmaf(d0, scale, -Dq), p1 * fmaf(d1, scale, -Dq));
             }
             pk[g * 4 + (t >> 1)] = pack_bf16(p0, p1);
           }
         }
-        if (c == 0 && i > 0) {
-          mbar_wait(&sm->mma_done, (uint32_t)(i - 1) & 1u);  // previous tile's MMAs have finished reading sP / sDS
+        if (c == 2 * half && i >= 2) {  // the MMAs of tile i-2 have finished reading this P / dS buffer
+          mbar_wait(&sm->mma_done[i & 1], (((uint32_t)i >> 1) - 1u) & 1u);
         }
         // row r of block (c >> 1): 16-byte pieces (c & 1) * 4 + g, XOR-swizzled with (r & 7)
         const uint32_t row_off = (uint32_t)(c >> 1) * 16384u + (uint32_t)r * 128u;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t piece = (uint32_t)(((c & 1) * 4 + g) ^ (r & 7)) * 16u;
-          *reinterpret_cast<uint4*>(sP + row_off + piece) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          *reinterpret_cast<uint4*>(sDS + row_off + piece) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+          st_shared_v4(aPbuf + row_off + piece, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          st_shared_v4(aPbuf + kPBytes + row_off + piece, dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
         }
       }
       tc_fence_before();
-      mbar_arrive(&sm->s_free);
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&sm->p_full);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sm->s_free);
+        mbar_arrive(&sm->p_full);
+      }
     }
     // ---- epilogue: dK_j, dV_j from TMEM -> bf16 rows of dqkv ----
-    mbar_wait(&sm->mma_done, (uint32_t)(nq - 1) & 1u);
+    mbar_wait(&sm->mma_done[(nq - 1) & 1], ((uint32_t)(nq - 1) >> 1) & 1u);
     tc_fence_after();
     const int kv = kv0 + r;
     __nv_bfloat16* drow = dqkv + ((long long)b * N + kv) * (3LL * D) + h * kHdB;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {  // 0: dK -> cols [D, 2D), 1: dV -> cols [2D, 3D)
+    {  // key half 0 stores dK -> cols [D, 2D), half 1 stores dV -> cols [2D, 3D)
+      const int which = half;
       const uint32_t tsrc = which == 0 ? tDK : tDV;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -286,14 +316,14 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ============================ dQ drain warps ============================
-    const int qd = warp - 8;  // TMEM lane quarter (warp % 4)
+    const int qd = warp - 12;  // TMEM lane quarter (warp % 4)
     const int r = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     float* acc_bh = dqacc + ((long long)b * H + h) * nq * (16LL * 128 * 4);
     for (int i = 0; i < nq; ++i) {
-      mbar_wait(&sm->dq_full, (uint32_t)i & 1u);
+      mbar_wait_backoff(&sm->dq_full, (uint32_t)i & 1u);
       tc_fence_after();
       uint32_t o0[32], o1[32];
       tmem_ld32(tDQ + lane_off, o0);
@@ -319,7 +349,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -353,11 +383,13 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   float* dqacc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + ws_dvec_bytes(B, N, H));
   const size_t dq_bytes = (size_t)B * H * nq * 16 * 128 * 4 * sizeof(float);
 
-  constexpr int smem_bytes = 2 * kTileBytesB + 4 * kTileBytesB + 2 * kPBytes + 1024 + 256;
+  constexpr int smem_bytes = 2 * kTileBytesB + 4 * kTileBytesB + 4 * kPBytes + 1024 + 256;  // 225.25 KB
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(tc_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    attr_err = cudaFuncSetAttribute(tc_attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(tc_attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   });
   if (attr_err != cudaSuccess)
     return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
@@ -375,8 +407,11 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   if ((rc = make_tok_tmap(&tm_do, dout, B, N, D)) != TVIT_OK) return rc;
   dim3 grid(nq, H, B);
   const float scale = 1.0f / sqrtf((float)hd);
-  tc_attn_bwd_kernel<<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, lse, dvec, dqacc,
-                                                               (__nv_bfloat16*)dqkv, N, H, scale, make_drop(drop));
+  const DropCfg dc = make_drop(drop);
+  if (dc.thr16 != 0)
+    tc_attn_bwd_kernel<true><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, N, H, scale, dc);
+  else
+    tc_attn_bwd_kernel<false><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, N, H, scale, dc);
   TVIT_LAUNCH_OK();
   {
     const long long total = (long long)B * H * nq * 16 * 128;

@@ -22,6 +22,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -73,15 +77,38 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef TVIT_MBAR_TIMEOUT_NS
 #define TVIT_MBAR_TIMEOUT_NS 4000000000ull
 #endif
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t parity) {
+  printf("tvit: mbarrier wait timed out (block %d,%d,%d thread %d parity %u)\n", (int)blockIdx.x, (int)blockIdx.y,
+         (int)blockIdx.z, (int)threadIdx.x, parity);
+  __trap();
+}
+// NOTE: %globaltimer is only sampled every 4096 failed polls -- reading it on every wait costs hundreds of
+// cycles and was the dominant cost of short pipeline hand-offs.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = globaltimer_ns();
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0u && globaltimer_ns() - t0 > TVIT_MBAR_TIMEOUT_NS) {
-      printf("tvit: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
-             parity);
-      __trap();
+    if ((++spins & 0xfffu) == 0u) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TVIT_MBAR_TIMEOUT_NS) mbar_timeout_trap(parity);
+    }
+  }
+}
+
+// Same, for waiters that are off the critical path (TMA producer, drain warps): sleep between polls so the
+// spin loop does not steal issue slots from the math warps sharing the scheduler.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if ((++spins & 0xfffu) == 0u) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TVIT_MBAR_TIMEOUT_NS) mbar_timeout_trap(parity);
     }
   }
 }

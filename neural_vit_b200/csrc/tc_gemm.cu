@@ -5,7 +5,8 @@
 //   warp 0   TMA producer    (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1   MMA issuer      (one elected thread: tcgen05.mma cta_group::1, 128 x BN x 16 per instruction)
 //   warp 2   TMEM allocator  (2 accumulator stages x BN fp32 columns)
-//   warps 4-7 epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global), overlapped with
+//   warps 4-11 epilogue      (8 warps: TMEM lane quarter = warp % 4, column half = (warp - 4) / 4;
+//                            tcgen05.ld 32x32b -> registers -> fused epilogue -> global), overlapped with
 //                            the next tile's main loop through the double-buffered TMEM accumulator.
 // Operand layouts:
 //   K-major (trans == 0): box {64 k, rows} -> rows of 128 B, 8-row swizzle atoms (SBO 1024).
@@ -69,7 +70,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // ------------------------------------------------------------------------------------------
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiThreads = 256;
 
 template <int BN>
 struct GemmCfg {
@@ -119,7 +121,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -210,7 +212,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
+    const int q = warp & 3;            // TMEM lane quarter == warp_id % 4
+    const int half = (warp - 4) >> 2;  // which half of the tile's 32-column chunks this warp drains
+    constexpr int kChunks = BN / 32, kHalfChunks = kChunks / 2;
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const int tile = w / sh.splits;
@@ -222,7 +226,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * kHalfChunks; c < (half + 1) * kHalfChunks; ++c) {
         if (n0 + c * 32 >= sh.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), r);

@@ -90,8 +90,8 @@ def test_against_fp64_oracle(tag, kw, batch, precision):
     else:
         assert rel_err(logits, rl) < BF16_TOL
         tol = BF16_TOL
-    worst = max((rel_err(grads[k], rg[k]), k) for k in rg)
-    assert worst[0] < tol, worst
+    errs = sorted(((rel_err(grads[k], rg[k]), k) for k in rg), reverse=True)
+    assert errs[0][0] < tol, errs[:6]
 
 
 def test_eval_mode_is_deterministic_and_dropout_free():

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python tools/prof_attn.py > gpurun_out/prof_attn_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"tc_attn" -s 2 -c 2 -o gpurun_out/prof_attn -f python tools/prof_attn.py > gpurun_out/ncu_attn.log 2>&1
+echo "ncu exit $?"; tail -n 3 gpurun_out/ncu_attn.log
