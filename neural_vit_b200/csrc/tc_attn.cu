@@ -39,7 +39,8 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
   uint8_t* sKV = smem + kTileBytes;  // stage s: K at sKV + s*2*kTileBytes, V right after K
   AttnFwdSmem* sm = reinterpret_cast<AttnFwdSmem*>(smem + 5 * kTileBytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int D = H * kHd;
   const int q0 = qt * kTile;
@@ -69,54 +70,63 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
 
   if (warp == 4) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
+    // warp-uniform loop; TMA instructions predicated on one elected lane (see the note in tc_gemm.cu)
+    if (elect_one()) {
       tma_prefetch_desc(&tm_qkv);
       mbar_expect_tx(&sm->q_full, kTileBytes);
       tma_load_3d(sQ, &tm_qkv, &sm->q_full, h * kHd, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&sm->kv_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
+    }
+    __syncwarp();
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      mbar_wait_backoff(&sm->kv_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(&sm->kv_full[st], 2 * kTileBytes);
         uint8_t* sK = sKV + st * 2 * kTileBytes;
         tma_load_3d(sK, &tm_qkv, &sm->kv_full[st], D + h * kHd, j * kTile, b);
         tma_load_3d(sK + kTileBytes, &tm_qkv, &sm->kv_full[st], 2 * D + h * kHd, j * kTile, b);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B = V: MN-major
-      const uint32_t aQ = smem_u32(sQ);
-      mbar_wait(&sm->q_full, 0);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&sm->kv_full[st], ((uint32_t)j >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(sKV + st * 2 * kTileBytes);
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B = V: MN-major
+    const uint32_t aQ = smem_u32(sQ);
+    mbar_wait(&sm->q_full, 0);
+    auto issue_s = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&sm->kv_full[st], ((uint32_t)j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t aK = smem_u32(sKV + st * 2 * kTileBytes);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kHd / 16; ++k)
           umma_ss(tS, umma_smem_desc(aQ + k * 32, 0, 1024), umma_smem_desc(aK + k * 32, 0, 1024), idesc_s,
                   k > 0 ? 1u : 0u);
         tc_commit(&sm->s_full);
-      };
-      issue_s(0);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        if (j + 1 < nkv) {
-          mbar_wait(&sm->s_free, (uint32_t)j & 1u);  // softmax_j holds S_j in registers
-          tc_fence_after();
-          issue_s(j + 1);
-        }
-        mbar_wait(&sm->p_full, (uint32_t)j & 1u);  // P_j in TMEM, O rescaled
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      if (j + 1 < nkv) {
+        mbar_wait(&sm->s_free, (uint32_t)j & 1u);  // softmax_j holds S_j in registers
         tc_fence_after();
-        const uint32_t aV = smem_u32(sKV + st * 2 * kTileBytes + kTileBytes);
+        issue_s(j + 1);
+      }
+      mbar_wait(&sm->p_full, (uint32_t)j & 1u);  // P_j in TMEM, O rescaled
+      tc_fence_after();
+      const uint32_t aV = smem_u32(sKV + st * 2 * kTileBytes + kTileBytes);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kTile / 16; ++k)
           umma_ts(tO, tP + k * 8, umma_smem_desc(aV + k * 2048, 16384, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(&sm->kv_empty[st]);
         tc_commit(&sm->pv_done);
       }
+      __syncwarp();
     }
   } else {
     // ============================ softmax warps ============================

@@ -107,7 +107,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = bars + 2 * Cfg::kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -138,7 +138,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // (warp-uniform loop; only the TMA instructions are predicated on one elected lane -- issuing UTMALDG /
+    //  UTCHMMA from divergent `if (lane == 0)` code makes ptxas wrap each one in an ELECT + R2UR loop)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -148,9 +150,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(kb0 + sh.kb_per_split, sh.k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
+          if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, m0);
           } else {
@@ -165,6 +168,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < BN / 64; ++j)
               tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * kBK);
           }
+          }
+          __syncwarp();
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -174,7 +179,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       const uint32_t a_lbo = sh.a_lbo, b_lbo = sh.b_lbo, a_sbo = sh.a_sbo, b_sbo = sh.b_sbo;
       const uint32_t a_kstep = sh.a_kstep, b_kstep = sh.b_kstep;  // bytes per UMMA_K = 16
@@ -195,19 +200,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
-            const uint64_t db = umma_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
-            umma_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t da = umma_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
+              const uint64_t db = umma_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
+              umma_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
           }
-          tc_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          __syncwarp();
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (elect_one()) tc_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
