@@ -195,7 +195,9 @@ __device__ __forceinline__ float drop_mult(const DropCfg& c, unsigned long long 
   uint32_t w[4];
   drop_bits8(c, e >> 3, w);
   const unsigned int j = (unsigned int)(e & 7ull);
-  const uint32_t bits = (w[j >> 1] >> ((j & 1u) * 16u)) & 0xffffu;
+  const unsigned int k = j >> 1;  // selects instead of a dynamic index: keeps w[] out of local memory
+  const uint32_t ww = k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3]));
+  const uint32_t bits = (ww >> ((j & 1u) * 16u)) & 0xffffu;
   return bits >= c.thr16 ? c.inv_keep : 0.0f;
 }
 

@@ -23,11 +23,12 @@ __device__ __forceinline__ void drop_mult4(const DropCfg& c, unsigned long long 
   }
   uint32_t w[4];
   drop_bits8(c, e >> 3, w);
-  const int h = (int)((e >> 2) & 1ull) * 2;
-  m[0] = ((w[h] & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
-  m[1] = ((w[h] >> 16) >= c.thr16) ? c.inv_keep : 0.f;
-  m[2] = ((w[h + 1] & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
-  m[3] = ((w[h + 1] >> 16) >= c.thr16) ? c.inv_keep : 0.f;
+  const bool hi = ((e >> 2) & 1ull) != 0ull;  // selects, not a dynamic index (keeps w[] in registers)
+  const uint32_t w0 = hi ? w[2] : w[0], w1 = hi ? w[3] : w[1];
+  m[0] = ((w0 & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
+  m[1] = ((w0 >> 16) >= c.thr16) ? c.inv_keep : 0.f;
+  m[2] = ((w1 & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
+  m[3] = ((w1 >> 16) >= c.thr16) ? c.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -61,14 +61,31 @@ __device__ __forceinline__ void drop_mult4e(const DropCfg& c, unsigned long long
   if ((e & 3ull) == 0ull) {
     uint32_t w[4];
     drop_bits8(c, e >> 3, w);
-    const int h = (int)((e >> 2) & 1ull) * 2;
-    m[0] = ((w[h] & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
-    m[1] = ((w[h] >> 16) >= c.thr16) ? c.inv_keep : 0.f;
-    m[2] = ((w[h + 1] & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
-    m[3] = ((w[h + 1] >> 16) >= c.thr16) ? c.inv_keep : 0.f;
+    const bool hi = ((e >> 2) & 1ull) != 0ull;  // selects, not a dynamic index (keeps w[] in registers)
+    const uint32_t w0 = hi ? w[2] : w[0], w1 = hi ? w[3] : w[1];
+    m[0] = ((w0 & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
+    m[1] = ((w0 >> 16) >= c.thr16) ? c.inv_keep : 0.f;
+    m[2] = ((w1 & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
+    m[3] = ((w1 >> 16) >= c.thr16) ? c.inv_keep : 0.f;
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) m[j] = drop_mult(c, e + j);
+  }
+}
+
+// 8 multipliers for e..e+7, e % 8 == 0: one Philox call
+__device__ __forceinline__ void drop_mult8(const DropCfg& c, unsigned long long e, float m[8]) {
+  if (c.thr16 == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = 1.0f;
+    return;
+  }
+  uint32_t w[4];
+  drop_bits8(c, e >> 3, w);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m[2 * j] = ((w[j] & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
+    m[2 * j + 1] = ((w[j] >> 16) >= c.thr16) ? c.inv_keep : 0.f;
   }
 }
 
@@ -195,8 +212,7 @@ __device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, co
       return;
     }
     float ml[8];
-    drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, ml);
-    drop_mult4e(p.drop, (unsigned long long)m * p.N + n0 + 4, ml + 4);
+    drop_mult8(p.drop, (unsigned long long)m * p.N + n0, ml);  // vec8_ok: N % 8 == 0 and n0 % 8 == 0
     if (EPI == TVIT_EPI_BIAS_GELU) {
       uint4 h = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
       *reinterpret_cast<uint4*>((__nv_bfloat16*)p.aux + m * p.ldaux + n0) = h;
@@ -218,6 +234,71 @@ __device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, co
   }
   epi_apply4<EPI, T>(p, m, n0, make_float4(v[0], v[1], v[2], v[3]));
   if (n0 + 4 < p.N) epi_apply4<EPI, T>(p, m, n0 + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core epilogue fast path: one thread owns 32 consecutive columns of one row (a tcgen05.ld 32x32b.x32
+// chunk).  The per-thread global operands of the RESIDUAL (fp32 residual row) and GELU_BWD (bf16 pre-activation)
+// epilogues are fetched into registers by `load()` BEFORE the TMEM load is waited for, so their latency
+// overlaps it; bias / gamma come from shared memory (staged once per tile by the GEMM kernel).
+// Requires p.vec8_ok, n0 + 32 <= p.N, bf16 activations.
+// ---------------------------------------------------------------------------------------------------------
+template <int EPI>
+struct EpiPrefetch32 {
+  float4 f[EPI == TVIT_EPI_RESIDUAL ? 8 : 1];
+  uint4 h[EPI == TVIT_EPI_GELU_BWD ? 4 : 1];
+  __device__ __forceinline__ void load(const EpiParams& p, int m, int n0) {
+    if (EPI == TVIT_EPI_RESIDUAL) {
+      const float* r = p.resid + m * p.ldres + n0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = ld4(r + 4 * j);
+    } else if (EPI == TVIT_EPI_GELU_BWD) {
+      const __nv_bfloat16* a = (const __nv_bfloat16*)p.aux + m * p.ldaux + n0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = *reinterpret_cast<const uint4*>(a + 8 * j);
+    }
+  }
+};
+
+template <int EPI>
+__device__ __forceinline__ void epi_apply32_pre(const EpiParams& p, int m, int n0, const uint32_t (&acc)[32],
+                                                const EpiPrefetch32<EPI>& pre) {
+  if (EPI == TVIT_EPI_RESIDUAL) {
+    const float rs = p.row_scale ? p.row_scale[m / p.rpg] : 1.0f;
+    float* o = (float*)p.out + m * p.ldo + n0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 v = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                             __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+      if (p.bias) {
+        const float4 b = ld4(p.bias + n0 + 4 * j);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      float mlt[4];
+      drop_mult4e(p.drop, (unsigned long long)m * p.N + n0 + 4 * j, mlt);
+      const float4 g = p.gamma ? ld4(p.gamma + n0 + 4 * j) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 r = pre.f[j];
+      st4(o + 4 * j, make_float4(r.x + rs * g.x * v.x * mlt[0], r.y + rs * g.y * v.y * mlt[1],
+                                 r.z + rs * g.z * v.z * mlt[2], r.w + rs * g.w * v.w * mlt[3]));
+    }
+  } else if (EPI == TVIT_EPI_GELU_BWD) {
+    __nv_bfloat16* o = (__nv_bfloat16*)p.out + m * p.ldo + n0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float ml[8];
+      drop_mult8(p.drop, (unsigned long long)m * p.N + n0 + 8 * j, ml);
+      const uint32_t hw[4] = {pre.h[j].x, pre.h[j].y, pre.h[j].z, pre.h[j].w};
+      float x[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[t]));
+        x[2 * t] = __uint_as_float(acc[8 * j + 2 * t]) * ml[2 * t] * gelu_grad_fast(f.x);
+        x[2 * t + 1] = __uint_as_float(acc[8 * j + 2 * t + 1]) * ml[2 * t + 1] * gelu_grad_fast(f.y);
+      }
+      *reinterpret_cast<uint4*>(o + 8 * j) =
+          make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    }
+  }
 }
 
 }  // namespace tvit

@@ -30,6 +30,7 @@ struct AttnFwdSmem {
   uint32_t tmem_base;
 };
 
+template <bool kDrop>
 __global__ void __launch_bounds__(kAttnFwdThreads, 2)
 tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
                    float* __restrict__ lse, int N, int H, float scale_log2, DropCfg drop) {
@@ -163,37 +164,35 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float m_new = fmaxf(m2, mx * scale_log2);  // running max in the scaled log2 domain
       const float corr = ex2_approx(m2 - m_new);
+      // exponentials, row sum (of the un-dropped probabilities), dropout mask and bf16 packing in one pass;
+      // the 1/(1-p) factor of kept elements is applied once to O in the epilogue
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      uint32_t pk[64];
+      const unsigned long long g0 = (rowe + (unsigned long long)j * kTile) >> 3;
+      const uint32_t thr_hi = drop.thr16 << 16;
 #pragma unroll
-      for (int c = 0; c < 128; c += 4) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[c]), scale_log2, -m_new));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[c + 1]), scale_log2, -m_new));
-        const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[c + 2]), scale_log2, -m_new));
-        const float p3 = ex2_approx(fmaf(__uint_as_float(sreg[c + 3]), scale_log2, -m_new));
-        rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-        sreg[c] = __float_as_uint(p0);
-        sreg[c + 1] = __float_as_uint(p1);
-        sreg[c + 2] = __float_as_uint(p2);
-        sreg[c + 3] = __float_as_uint(p3);
-      }
-      l = l * corr + ((rs0 + rs1) + (rs2 + rs3));
-      if (drop.thr16 != 0) {
-        const unsigned long long g0 = (rowe + (unsigned long long)j * kTile) >> 3;
+      for (int g = 0; g < 16; ++g) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (kDrop) drop_bits8(drop, g0 + g, w);
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          uint32_t w[4];
-          drop_bits8(drop, g0 + g, w);
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const uint32_t bits = (w[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
-            const float p = __uint_as_float(sreg[g * 8 + t]);
-            sreg[g * 8 + t] = __float_as_uint(bits >= drop.thr16 ? p * drop.inv_keep : 0.f);
+        for (int t = 0; t < 8; t += 4) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(sreg[g * 8 + t]), scale_log2, -m_new));
+          float p1 = ex2_approx(fmaf(__uint_as_float(sreg[g * 8 + t + 1]), scale_log2, -m_new));
+          float p2 = ex2_approx(fmaf(__uint_as_float(sreg[g * 8 + t + 2]), scale_log2, -m_new));
+          float p3 = ex2_approx(fmaf(__uint_as_float(sreg[g * 8 + t + 3]), scale_log2, -m_new));
+          rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+          if (kDrop) {  // 16 random bits per element: low half via (w << 16), high half via w itself
+            const uint32_t wa = w[t >> 1], wb = w[(t >> 1) + 1];
+            p0 = ((wa << 16) >= thr_hi) ? p0 : 0.f;
+            p1 = (wa >= thr_hi) ? p1 : 0.f;
+            p2 = ((wb << 16) >= thr_hi) ? p2 : 0.f;
+            p3 = (wb >= thr_hi) ? p3 : 0.f;
           }
+          pk[g * 4 + (t >> 1)] = pack_bf16(p0, p1);
+          pk[g * 4 + (t >> 1) + 1] = pack_bf16(p2, p3);
         }
       }
-      uint32_t pk[64];
-#pragma unroll
-      for (int c = 0; c < 64; ++c) pk[c] = pack_bf16(__uint_as_float(sreg[2 * c]), __uint_as_float(sreg[2 * c + 1]));
+      l = l * corr + ((rs0 + rs1) + (rs2 + rs3));
 
       if (j > 0) {
         mbar_wait(&sm->pv_done, (uint32_t)(j - 1) & 1u);  // O and the P buffer are free again
@@ -220,7 +219,7 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
     // ---- epilogue: O / l -> bf16, token-major store; LSE ----
     mbar_wait(&sm->pv_done, (uint32_t)(nkv - 1) & 1u);
     tc_fence_after();
-    const float inv = 1.0f / l;
+    const float inv = (kDrop ? drop.inv_keep : 1.0f) / l;
     __nv_bfloat16* orow = out + ((long long)b * N + q) * D + h * kHd;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -266,7 +265,9 @@ int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(tc_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    attr_err = cudaFuncSetAttribute(tc_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(tc_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   });
   if (attr_err != cudaSuccess)
     return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
@@ -275,8 +276,11 @@ int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int
   if (rc != TVIT_OK) return rc;
   dim3 grid((N + kTile - 1) / kTile, H, B);
   const float scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
-  tc_attn_fwd_kernel<<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, scale_log2,
-                                                               make_drop(drop));
+  const DropCfg dc = make_drop(drop);
+  if (dc.thr16 != 0)
+    tc_attn_fwd_kernel<true><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, scale_log2, dc);
+  else
+    tc_attn_fwd_kernel<false><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, scale_log2, dc);
   TVIT_LAUNCH_OK();
   return TVIT_OK;
 }

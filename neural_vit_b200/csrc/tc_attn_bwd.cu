@@ -23,7 +23,8 @@ constexpr int kHdB = 64;
 constexpr int kTileB = 128;
 constexpr int kTileBytesB = kTileB * kHdB * 2;  // 16384: one [128 x 64] bf16 operand tile
 constexpr int kPBytes = kTileB * kTileB * 2;    // 32768: one [128 x 128] bf16 P / dS tile (two 64-wide blocks)
-constexpr int kAttnBwdThreads = 512;  // warps 0-7 softmax, 8 TMA, 9 MMA, 12-15 dQ drain
+constexpr int kAttnBwdThreads = 768;  // warps 0-15 softmax, 16 TMA, 17 MMA (+TMEM alloc), 20-23 dQ drain
+constexpr int kSoftmaxWarps = 16;
 
 __host__ __device__ __forceinline__ unsigned long long attn_drop_row_base_b(int b, int H, int h, int N, int q) {
   const unsigned long long npad = (unsigned long long)((N + 7) & ~7);
@@ -110,15 +111,15 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_init(&sm->qdo_empty[i], 1);
     }
     mbar_init(&sm->s_full, 1);
-    mbar_init(&sm->s_free, 8);   // one elected arrive per softmax warp
-    mbar_init(&sm->p_full, 8);
+    mbar_init(&sm->s_free, kSoftmaxWarps);  // one elected arrive per softmax warp
+    mbar_init(&sm->p_full, kSoftmaxWarps);
     mbar_init(&sm->mma_done[0], 1);
     mbar_init(&sm->mma_done[1], 1);
     mbar_init(&sm->dq_full, 1);
     mbar_init(&sm->dq_free, 128);
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == 17) {
     tmem_alloc(&sm->tmem_base, 512);
     tmem_relinquish();
   }
@@ -131,7 +132,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   // Role code below is warp-uniform (all 32 lanes run the loops and the barrier waits); only the TMA / MMA /
   // commit instructions themselves are predicated on one elected lane.  Issuing them from divergent code
   // (`if (lane == 0)`) makes ptxas wrap every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST loop (~100 clk each).
-  if (warp == 8) {
+  if (warp == 16) {
     // ============================ TMA producer ============================
     if (elect_one()) {
       tma_prefetch_desc(&tm_qkv);
@@ -152,7 +153,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       __syncwarp();
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ============================ MMA issuer ============================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP: both operands K-major
     constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);    // dV, dK: A (sP/sDS) MN-major, B MN-major
@@ -217,9 +218,9 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       __syncwarp();
     }
-  } else if (warp < 8) {
+  } else if (warp < kSoftmaxWarps) {
     // ============ softmax warps: thread == query row (TMEM lane quarter warp % 4), key half warp / 4 ============
-    const int qd4 = warp & 3, half = warp >> 2;
+    const int qd4 = warp & 3, chunk = warp >> 2;  // 32 query rows x 32 keys per warp per tile
     const int r = qd4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd4 * 32) << 16;
     const float c_log2 = scale * 1.4426950408889634f;
@@ -240,16 +241,16 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_wait(&sm->s_full, (uint32_t)i & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 2 * half; c < 2 * half + 2; ++c) {
-        uint32_t sv[32], dp[32];
-        tmem_ld32(tS + lane_off + c * 32, sv);
-        tmem_ld32(tDP + lane_off + c * 32, dp);
+      for (int sc = 0; sc < 2; ++sc) {  // two 16-key sub-chunks keep the live register set small (16 warps / SM)
+        uint32_t sv[16], dp[16];
+        tmem_ld16(tS + lane_off + chunk * 32 + sc * 16, sv);
+        tmem_ld16(tDP + lane_off + chunk * 32 + sc * 16, dp);
         tmem_ld_wait();
-        uint32_t pk[16], dk[16];
+        uint32_t pk[8], dk[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint32_t w[4] = {0, 0, 0, 0};
-          if (kDrop) drop_bits8(drop, (rowe >> 3) + (unsigned long long)(c * 4 + g), w);
+          if (kDrop) drop_bits8(drop, (rowe >> 3) + (unsigned long long)(chunk * 4 + sc * 2 + g), w);
 #pragma unroll
           for (int t = 0; t < 8; t += 2) {
             float p0 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_log2, -lse2));
@@ -270,14 +271,14 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             pk[g * 4 + (t >> 1)] = pack_bf16(p0, p1);
           }
         }
-        if (c == 2 * half && i >= 2) {  // the MMAs of tile i-2 have finished reading this P / dS buffer
+        if (sc == 0 && i >= 2) {  // the MMAs of tile i-2 have finished reading this P / dS buffer
           mbar_wait(&sm->mma_done[i & 1], (((uint32_t)i >> 1) - 1u) & 1u);
         }
-        // row r of block (c >> 1): 16-byte pieces (c & 1) * 4 + g, XOR-swizzled with (r & 7)
-        const uint32_t row_off = (uint32_t)(c >> 1) * 16384u + (uint32_t)r * 128u;
+        // row r of 64-key block (chunk >> 1): 16-byte pieces (chunk & 1) * 4 + sc * 2 + g, XOR-swizzled with (r & 7)
+        const uint32_t row_off = (uint32_t)(chunk >> 1) * 16384u + (uint32_t)r * 128u;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t piece = (uint32_t)(((c & 1) * 4 + g) ^ (r & 7)) * 16u;
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t piece = (uint32_t)(((chunk & 1) * 4 + sc * 2 + g) ^ (r & 7)) * 16u;
           st_shared_v4(aPbuf + row_off + piece, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           st_shared_v4(aPbuf + kPBytes + row_off + piece, dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
         }
@@ -295,30 +296,27 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tc_fence_after();
     const int kv = kv0 + r;
     __nv_bfloat16* drow = dqkv + ((long long)b * N + kv) * (3LL * D) + h * kHdB;
-    {  // key half 0 stores dK -> cols [D, 2D), half 1 stores dV -> cols [2D, 3D)
-      const int which = half;
+    {  // warps with chunk 0/1 store dK columns [0,32)/[32,64) -> [D, 2D); chunk 2/3 store dV -> [2D, 3D)
+      const int which = chunk >> 1, c = chunk & 1;
       const uint32_t tsrc = which == 0 ? tDK : tDV;
+      uint32_t o[32];
+      tmem_ld32(tsrc + lane_off + c * 32, o);
+      tmem_ld_wait();
+      if (kv < N) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tsrc + lane_off + c * 32, o);
-        tmem_ld_wait();
-        if (kv < N) {
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(o[8 * t + 0]), __uint_as_float(o[8 * t + 1]));
-            v.y = pack_bf16(__uint_as_float(o[8 * t + 2]), __uint_as_float(o[8 * t + 3]));
-            v.z = pack_bf16(__uint_as_float(o[8 * t + 4]), __uint_as_float(o[8 * t + 5]));
-            v.w = pack_bf16(__uint_as_float(o[8 * t + 6]), __uint_as_float(o[8 * t + 7]));
-            *reinterpret_cast<uint4*>(drow + (which + 1) * D + c * 32 + 8 * t) = v;
-          }
+        for (int t = 0; t < 4; ++t) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[8 * t + 0]), __uint_as_float(o[8 * t + 1]));
+          v.y = pack_bf16(__uint_as_float(o[8 * t + 2]), __uint_as_float(o[8 * t + 3]));
+          v.z = pack_bf16(__uint_as_float(o[8 * t + 4]), __uint_as_float(o[8 * t + 5]));
+          v.w = pack_bf16(__uint_as_float(o[8 * t + 6]), __uint_as_float(o[8 * t + 7]));
+          *reinterpret_cast<uint4*>(drow + (which + 1) * D + c * 32 + 8 * t) = v;
         }
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 20) {
     // ============================ dQ drain warps ============================
-    const int qd = warp - 12;  // TMEM lane quarter (warp % 4)
+    const int qd = warp & 3;  // TMEM lane quarter (warp % 4)
     const int r = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     float* acc_bh = dqacc + ((long long)b * H + h) * nq * (16LL * 128 * 4);
@@ -349,7 +347,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

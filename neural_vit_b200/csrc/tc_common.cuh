@@ -73,6 +73,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware and is woken by the arrive.  Fewer polls
+// (less pressure on the MIO queue shared with st.shared / MUFU) at the price of a longer wake-up: used only by
+// waiters that are off the critical path.
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
 #ifndef TVIT_MBAR_TIMEOUT_NS
 #define TVIT_MBAR_TIMEOUT_NS 4000000000ull
@@ -103,9 +119,8 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   unsigned long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
-    if ((++spins & 0xfffu) == 0u) {
+  while (!mbar_try_wait_sleep(bar, parity)) {
+    if ((++spins & 0xffu) == 0u) {
       const unsigned long long now = globaltimer_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > TVIT_MBAR_TIMEOUT_NS) mbar_timeout_trap(parity);
@@ -207,6 +222,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

@@ -80,7 +80,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
+                                    4096 /*bias + gamma staging, 2 tiles x 2 x 256 fp32*/;
 };
 
 struct GemmShape {
@@ -106,6 +107,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
   uint64_t* tempty_bar = bars + 2 * Cfg::kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+  float* s_cols = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 stages][bias 256 | gamma 256]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -230,15 +232,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (tile / sh.n_tiles) * kBM, n0 = (tile % sh.n_tiles) * BN;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      // stage this tile's per-column vectors (bias, LayerScale gamma) in shared memory: one element per epilogue
+      // thread, double-buffered by accumulator stage; the named barrier also orders the buffer's previous readers
+      float* sb = s_cols + as * 512;
+      {
+        const int e = (int)threadIdx.x - 128;
+        const int col = n0 + e;
+        if (e < BN) {
+          sb[e] = (ep.bias && col < sh.N) ? ep.bias[col] : 0.f;
+          sb[256 + e] = (ep.gamma && col < sh.N) ? ep.gamma[col] : 1.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      EpiParams epl = ep;
+      if (ep.bias) epl.bias = sb - n0;
+      if (ep.gamma) epl.gamma = sb + 256 - n0;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      constexpr bool kPre = (EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_GELU_BWD);
 #pragma unroll 1
       for (int c = half * kHalfChunks; c < (half + 1) * kHalfChunks; ++c) {
-        if (n0 + c * 32 >= sh.N) break;  // warp-uniform
+        const int nc = n0 + c * 32;
+        if (nc >= sh.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), r);
+        if (kPre && ep.vec8_ok && nc + 32 <= sh.N) {
+          EpiPrefetch32<EPI> pre;
+          if (m < sh.M) pre.load(epl, m, nc);  // global operands in flight while the TMEM load completes
+          tmem_ld_wait();
+          if (m < sh.M) epi_apply32_pre<EPI>(epl, m, nc, r, pre);
+          continue;
+        }
         tmem_ld_wait();
         if (m < sh.M) {
 #pragma unroll
@@ -246,7 +272,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float v[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[8 * j + t]);
-            epi_apply8<EPI, __nv_bfloat16>(ep, m, n0 + c * 32 + 8 * j, v);
+            epi_apply8<EPI, __nv_bfloat16>(epl, m, nc + 8 * j, v);
           }
         }
       }
