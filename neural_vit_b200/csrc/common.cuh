@@ -97,6 +97,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // exact (erf) GELU and its derivative -- nn.GELU() default, reference model.py:137
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad_f(float x) {
@@ -110,12 +116,12 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 //   phi_cdf(x) = 0.5 erfc(-x / sqrt 2);   gelu = x * cdf;   gelu' = cdf + x * pdf
 __device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& pdf) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * z * z);  // exp(-x^2 / 2)
+  const float e = ex2_approx(-1.4426950408889634f * z * z);  // exp(-x^2 / 2)
   const float half_erfc = 0.5f * poly * t * e;          // 0.5 erfc(|x| / sqrt 2)
   cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
   pdf = 0.39894228040143268f * e;

@@ -237,66 +237,113 @@ __device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, co
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Tensor-core epilogue fast path: one thread owns 32 consecutive columns of one row (a tcgen05.ld 32x32b.x32
-// chunk).  The per-thread global operands of the RESIDUAL (fp32 residual row) and GELU_BWD (bf16 pre-activation)
-// epilogues are fetched into registers by `load()` BEFORE the TMEM load is waited for, so their latency
-// overlaps it; bias / gamma come from shared memory (staged once per tile by the GEMM kernel).
-// Requires p.vec8_ok, n0 + 32 <= p.N, bf16 activations.
+// Tensor-core epilogue fast path: one thread owns 16 consecutive columns of one row (a tcgen05.ld 32x32b.x16
+// sub-chunk).  Everything the epilogue reads is requested BEFORE the TMEM load is waited for, so all latencies
+// overlap: bias / LayerScale gamma come from shared memory (staged once per tile by the GEMM kernel, zero /
+// one filled when absent) through ld.shared, the per-thread operands of RESIDUAL (fp32 residual row) and
+// GELU_BWD (bf16 pre-activation) through 16-byte global loads.
+// Requires p.vec8_ok, nc + 16 <= p.N, bf16 activations.
 // ---------------------------------------------------------------------------------------------------------
-template <int EPI>
-struct EpiPrefetch32 {
-  float4 f[EPI == TVIT_EPI_RESIDUAL ? 8 : 1];
-  uint4 h[EPI == TVIT_EPI_GELU_BWD ? 4 : 1];
-  __device__ __forceinline__ void load(const EpiParams& p, int m, int n0) {
-    if (EPI == TVIT_EPI_RESIDUAL) {
-      const float* r = p.resid + m * p.ldres + n0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = ld4(r + 4 * j);
-    } else if (EPI == TVIT_EPI_GELU_BWD) {
-      const __nv_bfloat16* a = (const __nv_bfloat16*)p.aux + m * p.ldaux + n0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) h[j] = *reinterpret_cast<const uint4*>(a + 8 * j);
-    }
-  }
-};
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 
 template <int EPI>
-__device__ __forceinline__ void epi_apply32_pre(const EpiParams& p, int m, int n0, const uint32_t (&acc)[32],
-                                                const EpiPrefetch32<EPI>& pre) {
-  if (EPI == TVIT_EPI_RESIDUAL) {
-    const float rs = p.row_scale ? p.row_scale[m / p.rpg] : 1.0f;
-    float* o = (float*)p.out + m * p.ldo + n0;
+__device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, uint32_t s_gamma, float row_scale, int m,
+                                         int nc, uint32_t taddr, bool row_ok) {
+  constexpr bool kBias = (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL);
+  uint32_t acc[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
+        "=r"(acc[7]), "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]),
+        "=r"(acc[14]), "=r"(acc[15])
+      : "r"(taddr)
+      : "memory");
+  float4 b[4], g[4], res[4];
+  uint4 hx[2];
+  if (kBias) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 v = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
-                             __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
-      if (p.bias) {
-        const float4 b = ld4(p.bias + n0 + 4 * j);
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-      }
-      float mlt[4];
-      drop_mult4e(p.drop, (unsigned long long)m * p.N + n0 + 4 * j, mlt);
-      const float4 g = p.gamma ? ld4(p.gamma + n0 + 4 * j) : make_float4(1.f, 1.f, 1.f, 1.f);
-      const float4 r = pre.f[j];
-      st4(o + 4 * j, make_float4(r.x + rs * g.x * v.x * mlt[0], r.y + rs * g.y * v.y * mlt[1],
-                                 r.z + rs * g.z * v.z * mlt[2], r.w + rs * g.w * v.w * mlt[3]));
+    for (int j = 0; j < 4; ++j) b[j] = ld_shared_f4(s_bias + 16 * j);
+  }
+  if (EPI == TVIT_EPI_RESIDUAL) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] = ld_shared_f4(s_gamma + 16 * j);
+    if (row_ok) {
+      const float* r = p.resid + m * p.ldres + nc;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) res[j] = ld4(r + 4 * j);
     }
-  } else if (EPI == TVIT_EPI_GELU_BWD) {
-    __nv_bfloat16* o = (__nv_bfloat16*)p.out + m * p.ldo + n0;
+  }
+  if (EPI == TVIT_EPI_GELU_BWD && row_ok) {
+    const __nv_bfloat16* a = (const __nv_bfloat16*)p.aux + m * p.ldaux + nc;
+    hx[0] = *reinterpret_cast<const uint4*>(a);
+    hx[1] = *reinterpret_cast<const uint4*>(a + 8);
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (!row_ok) return;
+
+  float x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(acc[j]);
+  if (kBias) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float ml[8];
-      drop_mult8(p.drop, (unsigned long long)m * p.N + n0 + 8 * j, ml);
-      const uint32_t hw[4] = {pre.h[j].x, pre.h[j].y, pre.h[j].z, pre.h[j].w};
-      float x[8];
+      x[4 * j] += b[j].x; x[4 * j + 1] += b[j].y; x[4 * j + 2] += b[j].z; x[4 * j + 3] += b[j].w;
+    }
+  }
+  if (EPI == TVIT_EPI_STORE) {
+    __nv_bfloat16* o = (__nv_bfloat16*)p.out + m * p.ldo + nc;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      *reinterpret_cast<uint4*>(o + 8 * j) =
+          make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                     pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+    return;
+  }
+  float ml[16];
+  drop_mult8(p.drop, (unsigned long long)m * p.N + nc, ml);
+  drop_mult8(p.drop, (unsigned long long)m * p.N + nc + 8, ml + 8);
+  if (EPI == TVIT_EPI_BIAS_GELU) {
+    __nv_bfloat16* a = (__nv_bfloat16*)p.aux + m * p.ldaux + nc;
+    __nv_bfloat16* o = (__nv_bfloat16*)p.out + m * p.ldo + nc;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      *reinterpret_cast<uint4*>(a + 8 * j) =
+          make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                     pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = gelu_fast(x[j]) * ml[j];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      *reinterpret_cast<uint4*>(o + 8 * j) =
+          make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                     pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+  } else if (EPI == TVIT_EPI_RESIDUAL) {
+    float* o = (float*)p.out + m * p.ldo + nc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      st4(o + 4 * j, make_float4(res[j].x + row_scale * g[j].x * x[4 * j] * ml[4 * j],
+                                 res[j].y + row_scale * g[j].y * x[4 * j + 1] * ml[4 * j + 1],
+                                 res[j].z + row_scale * g[j].z * x[4 * j + 2] * ml[4 * j + 2],
+                                 res[j].w + row_scale * g[j].w * x[4 * j + 3] * ml[4 * j + 3]));
+  } else if (EPI == TVIT_EPI_GELU_BWD) {
+    __nv_bfloat16* o = (__nv_bfloat16*)p.out + m * p.ldo + nc;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t hw[4] = {hx[j].x, hx[j].y, hx[j].z, hx[j].w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[t]));
-        x[2 * t] = __uint_as_float(acc[8 * j + 2 * t]) * ml[2 * t] * gelu_grad_fast(f.x);
-        x[2 * t + 1] = __uint_as_float(acc[8 * j + 2 * t + 1]) * ml[2 * t + 1] * gelu_grad_fast(f.y);
+        x[8 * j + 2 * t] *= ml[8 * j + 2 * t] * gelu_grad_fast(f.x);
+        x[8 * j + 2 * t + 1] *= ml[8 * j + 2 * t + 1] * gelu_grad_fast(f.y);
       }
       *reinterpret_cast<uint4*>(o + 8 * j) =
-          make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+          make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                     pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
     }
   }
 }

@@ -244,35 +244,53 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      EpiParams epl = ep;
-      if (ep.bias) epl.bias = sb - n0;
-      if (ep.gamma) epl.gamma = sb + 256 - n0;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < sh.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      constexpr bool kPre = (EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_GELU_BWD);
+      constexpr bool kFast = (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL ||
+                              EPI == TVIT_EPI_GELU_BWD);
+      if (kFast && ep.vec8_ok) {
+        const float rsc = (EPI == TVIT_EPI_RESIDUAL && ep.row_scale && row_ok) ? ep.row_scale[m / ep.rpg] : 1.0f;
+        const uint32_t sb_addr = smem_u32(sb);
+        constexpr int kSub = BN / 16, kHalfSub = kSub / 2;
 #pragma unroll 1
-      for (int c = half * kHalfChunks; c < (half + 1) * kHalfChunks; ++c) {
-        const int nc = n0 + c * 32;
-        if (nc >= sh.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), r);
-        if (kPre && ep.vec8_ok && nc + 32 <= sh.N) {
-          EpiPrefetch32<EPI> pre;
-          if (m < sh.M) pre.load(epl, m, nc);  // global operands in flight while the TMEM load completes
-          tmem_ld_wait();
-          if (m < sh.M) epi_apply32_pre<EPI>(epl, m, nc, r, pre);
-          continue;
+        for (int u = half * kHalfSub; u < (half + 1) * kHalfSub; ++u) {
+          const int nc = n0 + u * 16;
+          if (nc >= sh.N) break;  // warp-uniform (N % 16 == 0 on this path is implied by vec8_ok only for N % 8;
+                                  // a trailing 8-column piece falls to the generic path below)
+          if (nc + 16 <= sh.N) {
+            tc_epi16<EPI>(ep, sb_addr + (uint32_t)(u * 64), sb_addr + 1024u + (uint32_t)(u * 64), rsc, m, nc,
+                          taddr + (uint32_t)(u * 16), row_ok);
+          } else {
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)(u * 16), r);
+            tmem_ld_wait();
+            if (row_ok) {
+              float v[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[t]);
+              epi_apply8<EPI, __nv_bfloat16>(ep, m, nc, v);
+            }
+          }
         }
-        tmem_ld_wait();
-        if (m < sh.M) {
+      } else {
+#pragma unroll 1
+        for (int c = half * kHalfChunks; c < (half + 1) * kHalfChunks; ++c) {
+          const int nc = n0 + c * 32;
+          if (nc >= sh.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+          if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float v[8];
+            for (int j = 0; j < 4; ++j) {
+              float v[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[8 * j + t]);
-            epi_apply8<EPI, __nv_bfloat16>(epl, m, nc + 8 * j, v);
+              for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[8 * j + t]);
+              epi_apply8<EPI, __nv_bfloat16>(ep, m, nc + 8 * j, v);
+            }
           }
         }
       }
