@@ -115,14 +115,14 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // two MUFU ops) -- far inside bf16 resolution; the fp32 verification path keeps erff above.
 //   phi_cdf(x) = 0.5 erfc(-x / sqrt 2);   gelu = x * cdf;   gelu' = cdf + x * pdf
 __device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& pdf) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = ex2_approx(-1.4426950408889634f * z * z);  // exp(-x^2 / 2)
-  const float half_erfc = 0.5f * poly * t * e;          // 0.5 erfc(|x| / sqrt 2)
+  // t = 1 / (1 + p |x| / sqrt2);  e = exp(-x^2/2);  0.5 erfc(|x|/sqrt2) = t (a1/2 + t (a2/2 + ...)) e
+  const float t = rcp_approx(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.0f));
+  const float e = ex2_approx(x * x * (-0.5f * 1.4426950408889634f));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float half_erfc = poly * t * e;
   cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
   pdf = 0.39894228040143268f * e;
 }

@@ -150,8 +150,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
     const float mu = mean[r], rs = rstd[r];
     const float* xr = x + r * xrs;
     const T* dyr = dy + r * (long long)D;
-    float4 xh[VPL], g[VPL];
+    float4 xh[VPL], g[VPL], gr[VPL];
     float s1 = 0.f, s2 = 0.f;
+    // all three streams (x, dy, residual gradient) are requested up front: one row = one round trip to HBM
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int vi = lane + 32 * j;
+      gr[j] = (gres && vi < nvec) ? ld4(gres + r * (long long)D + 4 * vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       const int vi = lane + 32 * j;
@@ -179,10 +185,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
         o.y = (g[j].y - c1 - xh[j].y * c2) * rs;
         o.z = (g[j].z - c1 - xh[j].z * c2) * rs;
         o.w = (g[j].w - c1 - xh[j].w * c2) * rs;
-        if (gres) {
-          const float4 gr = ld4(gres + r * (long long)D + 4 * vi);
-          o.x += gr.x; o.y += gr.y; o.z += gr.z; o.w += gr.w;
-        }
+        o.x += gr[j].x; o.y += gr[j].y; o.z += gr[j].z; o.w += gr[j].w;
         st4(dx + r * dxrs + 4 * vi, o);
         if (gp) {
           float m[4];

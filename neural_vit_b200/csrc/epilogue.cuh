@@ -24,6 +24,7 @@ struct EpiParams {
   int Kp, Fp, Tp;
   int vec_ok;   // N % 4 == 0 and every leading dimension % 4 == 0 -> 4-wide vector path is legal
   int vec8_ok;  // same with 8 (16-byte bf16 accesses)
+  int vec16_ok; // N, leading dimensions % 16 == 0 and 32-byte aligned bases: 256-bit (full-sector) accesses
 };
 
 inline EpiParams make_epi_params(const tvit_gemm_args* a) {
@@ -50,6 +51,9 @@ inline EpiParams make_epi_params(const tvit_gemm_args* a) {
   p.vec_ok = (a->N % 4 == 0) && (a->ldo % 4 == 0) && (a->aux == nullptr || a->ldaux % 4 == 0) &&
              (a->resid == nullptr || a->ldres % 4 == 0);
   p.vec8_ok = (a->N % 8 == 0) && (a->ldo % 8 == 0) && (a->aux == nullptr || a->ldaux % 8 == 0);
+  p.vec16_ok = (a->N % 16 == 0) && (a->ldo % 16 == 0) && (a->aux == nullptr || a->ldaux % 16 == 0) &&
+               (a->resid == nullptr || a->ldres % 16 == 0) && (((uintptr_t)a->out & 31u) == 0) &&
+               (((uintptr_t)a->aux & 31u) == 0) && (((uintptr_t)a->resid & 31u) == 0);
   return p;
 }
 
@@ -250,7 +254,26 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   return v;
 }
 
-template <int EPI>
+// 256-bit (one full 32-byte sector per thread) global accesses -- sm_100 STG/LDG.E.ENL2.256.  Sixteen-byte stores
+// from threads that own different rows reach L2 as half-written sectors and cap the output stream near 1.8 TB/s.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st_bf16x16(__nv_bfloat16* o, const float (&x)[16]) {
+  uint32_t v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+  st_global_v8(o, v);
+}
+
+template <int EPI, bool kDrop>
 __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, uint32_t s_gamma, float row_scale, int m,
                                          int nc, uint32_t taddr, bool row_ok) {
   constexpr bool kBias = (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL);
@@ -263,8 +286,8 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
         "=r"(acc[14]), "=r"(acc[15])
       : "r"(taddr)
       : "memory");
-  float4 b[4], g[4], res[4];
-  uint4 hx[2];
+  float4 b[4], g[4];
+  uint32_t res[16], hx[8];
   if (kBias) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) b[j] = ld_shared_f4(s_bias + 16 * j);
@@ -274,14 +297,12 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
     for (int j = 0; j < 4; ++j) g[j] = ld_shared_f4(s_gamma + 16 * j);
     if (row_ok) {
       const float* r = p.resid + m * p.ldres + nc;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) res[j] = ld4(r + 4 * j);
+      ld_global_v8(r, *reinterpret_cast<uint32_t(*)[8]>(&res[0]));
+      ld_global_v8(r + 8, *reinterpret_cast<uint32_t(*)[8]>(&res[8]));
     }
   }
   if (EPI == TVIT_EPI_GELU_BWD && row_ok) {
-    const __nv_bfloat16* a = (const __nv_bfloat16*)p.aux + m * p.ldaux + nc;
-    hx[0] = *reinterpret_cast<const uint4*>(a);
-    hx[1] = *reinterpret_cast<const uint4*>(a + 8);
+    ld_global_v8((const __nv_bfloat16*)p.aux + m * p.ldaux + nc, hx);
   }
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   if (!row_ok) return;
@@ -296,55 +317,40 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
     }
   }
   if (EPI == TVIT_EPI_STORE) {
-    __nv_bfloat16* o = (__nv_bfloat16*)p.out + m * p.ldo + nc;
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      *reinterpret_cast<uint4*>(o + 8 * j) =
-          make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                     pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+    st_bf16x16((__nv_bfloat16*)p.out + m * p.ldo + nc, x);
     return;
   }
   float ml[16];
-  drop_mult8(p.drop, (unsigned long long)m * p.N + nc, ml);
-  drop_mult8(p.drop, (unsigned long long)m * p.N + nc + 8, ml + 8);
-  if (EPI == TVIT_EPI_BIAS_GELU) {
-    __nv_bfloat16* a = (__nv_bfloat16*)p.aux + m * p.ldaux + nc;
-    __nv_bfloat16* o = (__nv_bfloat16*)p.out + m * p.ldo + nc;
+  if (kDrop) {
+    drop_mult8(p.drop, (unsigned long long)m * p.N + nc, ml);
+    drop_mult8(p.drop, (unsigned long long)m * p.N + nc + 8, ml + 8);
+  } else {
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
-      *reinterpret_cast<uint4*>(a + 8 * j) =
-          make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                     pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+    for (int j = 0; j < 16; ++j) ml[j] = 1.0f;  // folded away by the compiler
+  }
+  if (EPI == TVIT_EPI_BIAS_GELU) {
+    st_bf16x16((__nv_bfloat16*)p.aux + m * p.ldaux + nc, x);
 #pragma unroll
     for (int j = 0; j < 16; ++j) x[j] = gelu_fast(x[j]) * ml[j];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      *reinterpret_cast<uint4*>(o + 8 * j) =
-          make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                     pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+    st_bf16x16((__nv_bfloat16*)p.out + m * p.ldo + nc, x);
   } else if (EPI == TVIT_EPI_RESIDUAL) {
     float* o = (float*)p.out + m * p.ldo + nc;
+    const float gg[16] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w,
+                          g[2].x, g[2].y, g[2].z, g[2].w, g[3].x, g[3].y, g[3].z, g[3].w};
+    uint32_t ov[16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      st4(o + 4 * j, make_float4(res[j].x + row_scale * g[j].x * x[4 * j] * ml[4 * j],
-                                 res[j].y + row_scale * g[j].y * x[4 * j + 1] * ml[4 * j + 1],
-                                 res[j].z + row_scale * g[j].z * x[4 * j + 2] * ml[4 * j + 2],
-                                 res[j].w + row_scale * g[j].w * x[4 * j + 3] * ml[4 * j + 3]));
+    for (int j = 0; j < 16; ++j)
+      ov[j] = __float_as_uint(fmaf(row_scale * gg[j], x[j] * ml[j], __uint_as_float(res[j])));
+    st_global_v8(o, *reinterpret_cast<uint32_t(*)[8]>(&ov[0]));
+    st_global_v8(o + 8, *reinterpret_cast<uint32_t(*)[8]>(&ov[8]));
   } else if (EPI == TVIT_EPI_GELU_BWD) {
-    __nv_bfloat16* o = (__nv_bfloat16*)p.out + m * p.ldo + nc;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const uint32_t hw[4] = {hx[j].x, hx[j].y, hx[j].z, hx[j].w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[t]));
-        x[8 * j + 2 * t] *= ml[8 * j + 2 * t] * gelu_grad_fast(f.x);
-        x[8 * j + 2 * t + 1] *= ml[8 * j + 2 * t + 1] * gelu_grad_fast(f.y);
-      }
-      *reinterpret_cast<uint4*>(o + 8 * j) =
-          make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                     pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+    for (int t = 0; t < 8; ++t) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hx[t]));
+      x[2 * t] *= ml[2 * t] * gelu_grad_fast(f.x);
+      x[2 * t + 1] *= ml[2 * t + 1] * gelu_grad_fast(f.y);
     }
+    st_bf16x16((__nv_bfloat16*)p.out + m * p.ldo + nc, x);
   }
 }
 

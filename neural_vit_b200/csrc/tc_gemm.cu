@@ -94,7 +94,7 @@ struct GemmShape {
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool kDrop>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape sh,
                EpiParams ep) {
@@ -251,7 +251,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       constexpr bool kFast = (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL ||
                               EPI == TVIT_EPI_GELU_BWD);
-      if (kFast && ep.vec8_ok) {
+      if (kFast && ep.vec16_ok) {
         const float rsc = (EPI == TVIT_EPI_RESIDUAL && ep.row_scale && row_ok) ? ep.row_scale[m / ep.rpg] : 1.0f;
         const uint32_t sb_addr = smem_u32(sb);
         constexpr int kSub = BN / 16, kHalfSub = kSub / 2;
@@ -261,7 +261,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (nc >= sh.N) break;  // warp-uniform (N % 16 == 0 on this path is implied by vec8_ok only for N % 8;
                                   // a trailing 8-column piece falls to the generic path below)
           if (nc + 16 <= sh.N) {
-            tc_epi16<EPI>(ep, sb_addr + (uint32_t)(u * 64), sb_addr + 1024u + (uint32_t)(u * 64), rsc, m, nc,
+            tc_epi16<EPI, kDrop>(ep, sb_addr + (uint32_t)(u * 64), sb_addr + 1024u + (uint32_t)(u * 64), rsc, m, nc,
                           taddr + (uint32_t)(u * 16), row_ok);
           } else {
             uint32_t r[16];
@@ -310,10 +310,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // host launch
 // ------------------------------------------------------------------------------------------
-template <int BN, bool MN, int EPI>
-static int launch_tc(const tvit_gemm_args* a, const GemmShape& sh, const EpiParams& ep, cudaStream_t s) {
+template <int BN, bool MN, int EPI, bool kDrop>
+static int launch_tc_d(const tvit_gemm_args* a, const GemmShape& sh, const EpiParams& ep, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
-  auto kern = tc_gemm_kernel<BN, MN, MN, EPI>;
+  auto kern = tc_gemm_kernel<BN, MN, MN, EPI, kDrop>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -347,6 +347,14 @@ static int launch_tc(const tvit_gemm_args* a, const GemmShape& sh, const EpiPara
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, sh, ep);
   TVIT_LAUNCH_OK();
   return TVIT_OK;
+}
+
+template <int BN, bool MN, int EPI>
+static int launch_tc(const tvit_gemm_args* a, const GemmShape& sh, const EpiParams& ep, cudaStream_t s) {
+  constexpr bool kCanDrop = (EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_GELU_BWD ||
+                             EPI == TVIT_EPI_PATCH_EMBED);
+  if (kCanDrop && ep.drop.thr16 != 0) return launch_tc_d<BN, MN, EPI, kCanDrop>(a, sh, ep, s);
+  return launch_tc_d<BN, MN, EPI, false>(a, sh, ep, s);
 }
 
 template <int BN>
