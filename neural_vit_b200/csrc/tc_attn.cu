@@ -228,13 +228,12 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
       tmem_ld_wait();
       if (q < N) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(o[8 * t + 0]) * inv, __uint_as_float(o[8 * t + 1]) * inv);
-          v.y = pack_bf16(__uint_as_float(o[8 * t + 2]) * inv, __uint_as_float(o[8 * t + 3]) * inv);
-          v.z = pack_bf16(__uint_as_float(o[8 * t + 4]) * inv, __uint_as_float(o[8 * t + 5]) * inv);
-          v.w = pack_bf16(__uint_as_float(o[8 * t + 6]) * inv, __uint_as_float(o[8 * t + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 32 + 8 * t) = v;
+        for (int t = 0; t < 2; ++t) {  // 16 bf16 = one full 32-byte sector per store (D % 16 == 0)
+          uint32_t v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            v[u] = pack_bf16(__uint_as_float(o[16 * t + 2 * u]) * inv, __uint_as_float(o[16 * t + 2 * u + 1]) * inv);
+          st_global_b32x8(orow + c * 32 + 16 * t, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
         }
       }
     }

@@ -64,24 +64,30 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const 
 }
 
 // dq accumulator layout: [(b*H+h)][q tile][16 chunks][128 rows][4 fp32]
+// thread = (row r, group of 4 chunks): four coalesced float4 reads, one full-sector 32-byte bf16 store
 __global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_bfloat16* __restrict__ dqkv, int B,
                                           int N, int H, int nq) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long total = (long long)B * H * nq * 16 * 128;
+  const long long total = (long long)B * H * nq * 4 * 128;
   if (idx >= total) return;
   const int r = (int)(idx & 127);
-  const int c = (int)((idx >> 7) & 15);
-  const long long t = idx >> 11;  // (b*H+h)*nq + i
+  const int cg = (int)((idx >> 7) & 3);
+  const long long t = idx >> 9;  // (b*H+h)*nq + i
   const int i = (int)(t % nq);
   const long long bh = t / nq;
   const int h = (int)(bh % H), b = (int)(bh / H);
   const int q = i * kTileB + r;
   if (q >= N) return;
-  const float4 v = *reinterpret_cast<const float4*>(dqacc + idx * 4);
-  uint2 o;
-  o.x = pack_bf16(v.x, v.y);
-  o.y = pack_bf16(v.z, v.w);
-  *reinterpret_cast<uint2*>(dqkv + ((long long)b * N + q) * (3LL * H * kHdB) + h * kHdB + 4 * c) = o;
+  const float* src = dqacc + ((t * 16 + 4 * cg) * 128 + r) * 4;
+  uint32_t v[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 f = *reinterpret_cast<const float4*>(src + (long long)k * 512);
+    v[2 * k] = pack_bf16(f.x, f.y);
+    v[2 * k + 1] = pack_bf16(f.z, f.w);
+  }
+  st_global_b32x8(dqkv + ((long long)b * N + q) * (3LL * H * kHdB) + h * kHdB + 16 * cg, v[0], v[1], v[2], v[3], v[4],
+                  v[5], v[6], v[7]);
 }
 
 template <bool kDrop>
@@ -304,13 +310,12 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tmem_ld_wait();
       if (kv < N) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(o[8 * t + 0]), __uint_as_float(o[8 * t + 1]));
-          v.y = pack_bf16(__uint_as_float(o[8 * t + 2]), __uint_as_float(o[8 * t + 3]));
-          v.z = pack_bf16(__uint_as_float(o[8 * t + 4]), __uint_as_float(o[8 * t + 5]));
-          v.w = pack_bf16(__uint_as_float(o[8 * t + 6]), __uint_as_float(o[8 * t + 7]));
-          *reinterpret_cast<uint4*>(drow + (which + 1) * D + c * 32 + 8 * t) = v;
+        for (int t = 0; t < 2; ++t) {  // 16 bf16 = one full 32-byte sector per store
+          uint32_t v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            v[u] = pack_bf16(__uint_as_float(o[16 * t + 2 * u]), __uint_as_float(o[16 * t + 2 * u + 1]));
+          st_global_b32x8(drow + (which + 1) * D + c * 32 + 16 * t, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
         }
       }
     }
@@ -412,7 +417,7 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
     tc_attn_bwd_kernel<false><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, N, H, scale, dc);
   TVIT_LAUNCH_OK();
   {
-    const long long total = (long long)B * H * nq * 16 * 128;
+    const long long total = (long long)B * H * nq * 4 * 128;
     attn_bwd_dq_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dqacc, (__nv_bfloat16*)dqkv, B, N, H, nq);
     TVIT_LAUNCH_OK();
   }
