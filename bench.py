@@ -283,9 +283,12 @@ def main():
     if args.breakdown and rank == 0:
         names = ["attn_fwd", "attn_bwd"] + [f"gemm_e{i}" for i in range(6)] + ["gemm_e4_tn"]
         ops.TIMED = {n: [] for n in names}
+        if os.environ.get("TVIT_BENCH_DETAIL"):
+            ops.TIMED = {"detail": []}
         step(x_dev, y_dev)
         torch.cuda.synchronize()
-        breakdown = {n: round(sum(s.elapsed_time(e) for s, e in v), 3) for n, v in ops.TIMED.items() if v}
+        breakdown = {n: (round(sum(s.elapsed_time(e) for s, e in v), 3), len(v)) if "detail" in ops.TIMED
+                     else round(sum(s.elapsed_time(e) for s, e in v), 3) for n, v in ops.TIMED.items() if v}
         ops.TIMED = None
         print("per-op ms in one step:", json.dumps(breakdown), file=sys.stderr)
 

@@ -70,8 +70,13 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // ------------------------------------------------------------------------------------------
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 384;
-constexpr int kEpiThreads = 256;
+// epilogue warps: 4 TMEM lane quarters x column groups (BN = 192 -> 3 groups of 64 columns, else 2 halves)
+template <int BN> struct EpiCfg {
+  static constexpr int kGroups = (BN == 192) ? 3 : 2;
+  static constexpr int kEpiThreads = 128 * kGroups;
+  static constexpr int kThreads = 128 + kEpiThreads;
+};
+constexpr int kMaxResKBlocks = 6;  // weight-stationary variant: K <= 384
 
 template <int BN>
 struct GemmCfg {
@@ -94,19 +99,27 @@ struct GemmShape {
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool kDrop>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, bool A_MN, bool B_MN, int EPI, bool kDrop, bool B_RES>
+__global__ void __launch_bounds__(EpiCfg<BN>::kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape sh,
                EpiParams ep) {
+  // B_RES ("weight-stationary", K <= 384): this CTA keeps one n-tile of B (all k-blocks) resident in shared
+  // memory and streams only A, which removes ~60 % of the L2 -> SM operand traffic that bounds the K = 384 GEMMs.
   using Cfg = GemmCfg<BN>;
+  constexpr int kStages = B_RES ? 4 : Cfg::kStages;
+  constexpr int kStageBytes = B_RES ? Cfg::kABytes : Cfg::kStageBytes;
+  constexpr int kBResBytes = B_RES ? kMaxResKBlocks * Cfg::kBBytes : 0;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_all = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_bres = smem_all;            // [k_blocks][BN x 64] bf16, only with B_RES
+  uint8_t* smem = smem_all + kBResBytes;  // operand ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + Cfg::kStages;
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
-  uint64_t* tempty_bar = bars + 2 * Cfg::kStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;
+  uint64_t* bres_bar = bars + 2 * kStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
   float* s_cols = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 stages][bias 256 | gamma 256]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
@@ -117,13 +130,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < Cfg::kStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
+    mbar_init(bres_bar, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&tempty_bar[i], EpiCfg<BN>::kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -137,6 +151,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_work = sh.m_tiles * sh.n_tiles * sh.splits;
+  // work-item sequence of this CTA: round-robin over all items, or (B_RES) a fixed n-tile and strided m-tiles
+  int w_first = blockIdx.x, w_step = gridDim.x;
+  if (B_RES) {
+    const int n_fixed = blockIdx.x % sh.n_tiles, g = blockIdx.x / sh.n_tiles;
+    const int G = ((int)gridDim.x - n_fixed + sh.n_tiles - 1) / sh.n_tiles;  // CTAs sharing this n-tile
+    w_first = g * sh.n_tiles + n_fixed;
+    w_step = G * sh.n_tiles;
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -145,17 +167,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      if (B_RES && w_first < total_work) {
+        if (elect_one()) {
+          const int n0 = (w_first % sh.n_tiles) * BN;
+          mbar_expect_tx(bres_bar, (uint32_t)(sh.k_blocks * Cfg::kBBytes));
+          for (int kb = 0; kb < sh.k_blocks; ++kb)
+            tma_load_2d(s_bres + kb * Cfg::kBBytes, &tmB, bres_bar, kb * kBK, n0);
+        }
+        __syncwarp();
+      }
+      for (int w = w_first; w < total_work; w += w_step) {
         const int tile = w / sh.splits, split = w - tile * sh.splits;
         const int m0 = (tile / sh.n_tiles) * kBM, n0 = (tile % sh.n_tiles) * BN;
         const int kb0 = split * sh.kb_per_split;
         const int kb1 = min(kb0 + sh.kb_per_split, sh.k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if (elect_one()) {
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, m0);
           } else {
@@ -163,7 +194,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < kBM / 64; ++j)
               tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, kb * kBK);
           }
-          if (!B_MN) {
+          if (B_RES) {
+            // B is resident
+          } else if (!B_MN) {
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, n0);
           } else {
 #pragma unroll
@@ -172,7 +205,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           }
           __syncwarp();
-          if (++stage == Cfg::kStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -188,7 +221,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      if (B_RES && w_first < total_work) mbar_wait(bres_bar, 0);
+      for (int w = w_first; w < total_work; w += w_step, ++it) {
         const int tile = w / sh.splits, split = w - tile * sh.splits;
         const int kb0 = split * sh.kb_per_split;
         const int kb1 = min(kb0 + sh.kb_per_split, sh.k_blocks);
@@ -200,8 +234,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = B_RES ? smem_u32(s_bres + kb * Cfg::kBBytes) : sa + Cfg::kABytes;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
@@ -212,7 +246,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
           }
           __syncwarp();
-          if (++stage == Cfg::kStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -224,10 +258,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;            // TMEM lane quarter == warp_id % 4
-    const int half = (warp - 4) >> 2;  // which half of the tile's 32-column chunks this warp drains
-    constexpr int kChunks = BN / 32, kHalfChunks = kChunks / 2;
+    const int half = (warp - 4) >> 2;  // column group of this warp
+    constexpr int kGroups = EpiCfg<BN>::kGroups;
+    constexpr int kChunks = BN / 32, kHalfChunks = kChunks / kGroups;
     int it = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+    for (int w = w_first; w < total_work; w += w_step, ++it) {
       const int tile = w / sh.splits;
       const int m0 = (tile / sh.n_tiles) * kBM, n0 = (tile % sh.n_tiles) * BN;
       const int as = it & 1;
@@ -242,7 +277,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           sb[e] = (ep.bias && col < sh.N) ? ep.bias[col] : 0.f;
           sb[256 + e] = (ep.gamma && col < sh.N) ? ep.gamma[col] : 1.f;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EpiCfg<BN>::kEpiThreads) : "memory");
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -254,7 +289,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (kFast && ep.vec16_ok) {
         const float rsc = (EPI == TVIT_EPI_RESIDUAL && ep.row_scale && row_ok) ? ep.row_scale[m / ep.rpg] : 1.0f;
         const uint32_t sb_addr = smem_u32(sb);
-        constexpr int kSub = BN / 16, kHalfSub = kSub / 2;
+        constexpr int kSub = BN / 16, kHalfSub = kSub / kGroups;
 #pragma unroll 1
         for (int u = half * kHalfSub; u < (half + 1) * kHalfSub; ++u) {
           const int nc = n0 + u * 16;
@@ -310,17 +345,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // host launch
 // ------------------------------------------------------------------------------------------
-template <int BN, bool MN, int EPI, bool kDrop>
+template <int BN, bool MN, int EPI, bool kDrop, bool B_RES = false>
 static int launch_tc_d(const tvit_gemm_args* a, const GemmShape& sh, const EpiParams& ep, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
-  auto kern = tc_gemm_kernel<BN, MN, MN, EPI, kDrop>;
+  auto kern = tc_gemm_kernel<BN, MN, MN, EPI, kDrop, B_RES>;
+  constexpr int kSmem = B_RES ? (kMaxResKBlocks * Cfg::kBBytes + 4 * Cfg::kABytes + 1024 + 256 + 4096) : Cfg::kSmemBytes;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   });
   if (attr_err != cudaSuccess)
-    return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+    return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", kSmem,
                 cudaGetErrorString(attr_err));
 
   CUtensorMap tmA, tmB;
@@ -344,7 +380,7 @@ static int launch_tc_d(const tvit_gemm_args* a, const GemmShape& sh, const EpiPa
   }
   const int total = sh.m_tiles * sh.n_tiles * sh.splits;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, sh, ep);
+  kern<<<grid, EpiCfg<BN>::kThreads, kSmem, s>>>(tmA, tmB, sh, ep);
   TVIT_LAUNCH_OK();
   return TVIT_OK;
 }
@@ -353,6 +389,15 @@ template <int BN, bool MN, int EPI>
 static int launch_tc(const tvit_gemm_args* a, const GemmShape& sh, const EpiParams& ep, cudaStream_t s) {
   constexpr bool kCanDrop = (EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_GELU_BWD ||
                              EPI == TVIT_EPI_PATCH_EMBED);
+  // weight-stationary variant: K-major, K <= 384, BN = 192 divides N, enough m-tiles to keep every CTA busy
+  constexpr bool kResOk = (BN == 192) && !MN &&
+                          (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL ||
+                           EPI == TVIT_EPI_GELU_BWD);
+  if (kResOk && sh.k_blocks <= kMaxResKBlocks && sh.N % 192 == 0 && sh.m_tiles >= 2 * num_sms() &&
+      getenv("TVIT_NO_BRES") == nullptr) {
+    if (kCanDrop && ep.drop.thr16 != 0) return launch_tc_d<BN, MN, EPI, kCanDrop, kResOk>(a, sh, ep, s);
+    return launch_tc_d<BN, MN, EPI, false, kResOk>(a, sh, ep, s);
+  }
   if (kCanDrop && ep.drop.thr16 != 0) return launch_tc_d<BN, MN, EPI, kCanDrop>(a, sh, ep, s);
   return launch_tc_d<BN, MN, EPI, false>(a, sh, ep, s);
 }
@@ -395,6 +440,7 @@ int tc_gemm(const tvit_gemm_args* a, cudaStream_t s) {
       best_bn = bn;
     }
   }
+  if (!a->trans_a && a->K <= kMaxResKBlocks * kBK && a->N % 192 == 0) best_bn = 192;  // weight-stationary path
   GemmShape sh;
   sh.M = a->M;
   sh.N = a->N;

@@ -33,7 +33,9 @@ def _count(name: str) -> None:
 class _timed:
     def __init__(self, name):
         self.name = name
-        self.on = TIMED is not None and name in TIMED
+        self.on = TIMED is not None and (name in TIMED or "detail" in TIMED)
+        if self.on and name not in TIMED:
+            TIMED[name] = []
 
     def __enter__(self):
         if self.on:
@@ -112,7 +114,8 @@ def gemm(engine: int, dtype: int, a: torch.Tensor, b: torch.Tensor, M: int, N: i
         args.Kp, args.Fp, args.Tp = grid3
     args.split_k = split_k
     _count("gemm")
-    with _timed("gemm_e%d%s" % (epilogue, "_tn" if trans_a else "")):
+    with _timed(("gemm_e%d%s" % (epilogue, "_tn" if trans_a else "")) if TIMED is None or "detail" not in TIMED
+                else "gemm_e%d%s_N%d_K%d" % (epilogue, "_tn" if trans_a else "", N, K)):
         L.check(L.load().tvit_gemm(ctypes.byref(args), _stream()), "tvit_gemm")
 
 
