@@ -15,7 +15,7 @@ namespace tvit {
 
 constexpr int kHd = 64;
 constexpr int kTile = 128;
-constexpr int kAttnFwdThreads = 192;
+constexpr int kAttnFwdThreads = 320;  // warps 0-7 softmax (2 threads per query row), 8 TMA, 9 MMA
 constexpr int kTileBytes = kTile * kHd * 2;  // 16384
 
 // attention-dropout element index: row-major over (b, h, q, k) with the k extent padded to a multiple of 8
@@ -28,6 +28,7 @@ __host__ __device__ __forceinline__ unsigned long long attn_drop_row_base(int b,
 struct AttnFwdSmem {
   uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, pv_done;
   uint32_t tmem_base;
+  float xchg[2][2][128];  // [tile parity][key half][row]: partner exchange of row maxima (and final row sums)
 };
 
 template <bool kDrop>
@@ -54,12 +55,12 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
       mbar_init(&sm->kv_empty[i], 1);
     }
     mbar_init(&sm->s_full, 1);
-    mbar_init(&sm->s_free, 128);
-    mbar_init(&sm->p_full, 128);
+    mbar_init(&sm->s_free, 8);  // one elected arrive per softmax warp
+    mbar_init(&sm->p_full, 8);
     mbar_init(&sm->pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(&sm->tmem_base, 256);
     tmem_relinquish();
   }
@@ -69,7 +70,7 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
   const uint32_t tmem = sm->tmem_base;
   const uint32_t tS = tmem, tO = tmem + 128, tP = tmem + 192;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================ TMA producer ============================
     // warp-uniform loop; TMA instructions predicated on one elected lane (see the note in tc_gemm.cu)
     if (elect_one()) {
@@ -89,7 +90,7 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
       }
       __syncwarp();
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================ MMA issuer ============================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B = V: MN-major
@@ -131,100 +132,127 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
     }
   } else {
     // ============================ softmax warps ============================
-    const int r = warp * 32 + lane;  // query row within the tile == TMEM lane
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    // Two threads per query row: warp w owns TMEM lane quarter (w & 3) and key half (w >> 2), i.e. 64 of the
+    // tile's 128 keys.  Pass A reads the 64 scores only to find the row maximum (partners exchange it through
+    // smem, one 256-thread named barrier per tile); pass B re-reads them from TMEM 32 at a time and turns them
+    // into bf16 probabilities.  Nothing but 32 scores is ever live in registers, so 16 softmax warps per SM
+    // (2 CTAs) fit without spilling and hide each other's MUFU / TMEM latencies.  Each thread keeps a partial
+    // row sum; the partners' sums are combined once at the end.
+    const int qd4 = warp & 3, hf = warp >> 2;
+    const int r = qd4 * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(qd4 * 32) << 16;
     const int q = q0 + r;
     float m2 = -INFINITY, l = 0.f;
     const unsigned long long rowe = attn_drop_row_base(b, H, h, N, q < N ? q : 0);
+    const uint32_t thr_hi = drop.thr16 << 16;
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&sm->s_full, (uint32_t)j & 1u);
       tc_fence_after();
-      uint32_t sreg[128];
+      const int valid = N - j * kTile - hf * 64;  // keys beyond N are masked (last tile only)
+      // ---- pass A: row maximum of this thread's 64 scores ----
+      float mx;
+      {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tS + lane_off + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&sm->s_free);
-
-      const int valid = N - j * kTile;  // keys beyond N are masked (last tile only)
-      if (valid < kTile) {
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t sv[32];
+          tmem_ld32(tS + lane_off + hf * 64 + c2 * 32, sv);
+          tmem_ld_wait();
+          if (valid < 64) {
 #pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if (c >= valid) sreg[c] = 0xff800000u;  // -inf
-      }
-      // ~4.5 instructions per element: FMNMX, FFMA, MUFU.EX2, FADD, half a CVT
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 128; c += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sreg[c]));
-        mx1 = fmaxf(mx1, __uint_as_float(sreg[c + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sreg[c + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sreg[c + 3]));
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      const float m_new = fmaxf(m2, mx * scale_log2);  // running max in the scaled log2 domain
-      const float corr = ex2_approx(m2 - m_new);
-      // exponentials, row sum (of the un-dropped probabilities), dropout mask and bf16 packing in one pass;
-      // the 1/(1-p) factor of kept elements is applied once to O in the epilogue
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-      uint32_t pk[64];
-      const unsigned long long g0 = (rowe + (unsigned long long)j * kTile) >> 3;
-      const uint32_t thr_hi = drop.thr16 << 16;
-#pragma unroll
-      for (int g = 0; g < 16; ++g) {
-        uint32_t w[4] = {0, 0, 0, 0};
-        if (kDrop) drop_bits8(drop, g0 + g, w);
-#pragma unroll
-        for (int t = 0; t < 8; t += 4) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(sreg[g * 8 + t]), scale_log2, -m_new));
-          float p1 = ex2_approx(fmaf(__uint_as_float(sreg[g * 8 + t + 1]), scale_log2, -m_new));
-          float p2 = ex2_approx(fmaf(__uint_as_float(sreg[g * 8 + t + 2]), scale_log2, -m_new));
-          float p3 = ex2_approx(fmaf(__uint_as_float(sreg[g * 8 + t + 3]), scale_log2, -m_new));
-          rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-          if (kDrop) {  // 16 random bits per element: low half via (w << 16), high half via w itself
-            const uint32_t wa = w[t >> 1], wb = w[(t >> 1) + 1];
-            p0 = ((wa << 16) >= thr_hi) ? p0 : 0.f;
-            p1 = (wa >= thr_hi) ? p1 : 0.f;
-            p2 = ((wb << 16) >= thr_hi) ? p2 : 0.f;
-            p3 = (wb >= thr_hi) ? p3 : 0.f;
+            for (int c = 0; c < 32; ++c)
+              if (c2 * 32 + c >= valid) sv[c] = 0xff800000u;  // -inf
           }
-          pk[g * 4 + (t >> 1)] = pack_bf16(p0, p1);
-          pk[g * 4 + (t >> 1) + 1] = pack_bf16(p2, p3);
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(sv[c]));
+            mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
+          }
         }
+        mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       }
-      l = l * corr + ((rs0 + rs1) + (rs2 + rs3));
+      sm->xchg[j & 1][hf][r] = mx;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float mxo = sm->xchg[j & 1][hf ^ 1][r];
+      const float m_new = fmaxf(m2, fmaxf(mx, mxo) * scale_log2);  // running max in the scaled log2 domain
+      const float corr = ex2_approx(m2 - m_new);
 
       if (j > 0) {
         mbar_wait(&sm->pv_done, (uint32_t)(j - 1) & 1u);  // O and the P buffer are free again
         tc_fence_after();
-        if (__any_sync(0xffffffffu, m_new > m2)) {  // warp-uniform: rescale the running output
+        if (__any_sync(0xffffffffu, m_new > m2)) {  // warp-uniform: rescale this thread's 32 columns of O
           uint32_t o[32];
+          tmem_ld32(tO + lane_off + hf * 32, o);
+          tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            tmem_ld32(tO + lane_off + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * corr);
-            tmem_st32(tO + lane_off + c * 32, o);
-          }
+          for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * corr);
+          tmem_st32(tO + lane_off + hf * 32, o);
         }
       }
+      // ---- pass B: exponentials, partial row sum (of the un-dropped probabilities), dropout mask, bf16 pack ----
+      // (the 1/(1-p) factor of kept elements is applied once to O in the epilogue)
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      const unsigned long long g0 = (rowe + (unsigned long long)j * kTile + hf * 64) >> 3;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t sv[32];
+        tmem_ld32(tS + lane_off + hf * 64 + c2 * 32, sv);
+        tmem_ld_wait();
+        if (c2 == 1) {  // both halves of S are now in registers / consumed: release the S buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm->s_free);
+        }
+        if (valid < 64) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c2 * 32 + c >= valid) sv[c] = 0xff800000u;  // -inf
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[4] = {0, 0, 0, 0};
+          if (kDrop) drop_bits8(drop, g0 + c2 * 4 + g, w);
+#pragma unroll
+          for (int t = 0; t < 8; t += 4) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), scale_log2, -m_new));
+            float p1 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t + 1]), scale_log2, -m_new));
+            float p2 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t + 2]), scale_log2, -m_new));
+            float p3 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t + 3]), scale_log2, -m_new));
+            rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+            if (kDrop) {  // 16 random bits per element: low half via (w << 16), high half via w itself
+              const uint32_t wa = w[t >> 1], wb = w[(t >> 1) + 1];
+              p0 = ((wa << 16) >= thr_hi) ? p0 : 0.f;
+              p1 = (wa >= thr_hi) ? p1 : 0.f;
+              p2 = ((wb << 16) >= thr_hi) ? p2 : 0.f;
+              p3 = (wb >= thr_hi) ? p3 : 0.f;
+            }
+            pk[g * 4 + (t >> 1)] = pack_bf16(p0, p1);
+            pk[g * 4 + (t >> 1) + 1] = pack_bf16(p2, p3);
+          }
+        }
+        tmem_st16(tP + lane_off + hf * 32 + c2 * 16, pk);
+      }
+      l = l * corr + ((rs0 + rs1) + (rs2 + rs3));
       m2 = m_new;
-      tmem_st32(tP + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-      tmem_st32(tP + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&sm->p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->p_full);
     }
-    // ---- epilogue: O / l -> bf16, token-major store; LSE ----
+    // ---- epilogue: combine the partners' row sums; O / l -> bf16, token-major store; LSE ----
+    sm->xchg[nkv & 1][hf][r] = l;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    l += sm->xchg[nkv & 1][hf ^ 1][r];
     mbar_wait(&sm->pv_done, (uint32_t)(nkv - 1) & 1u);
     tc_fence_after();
     const float inv = (kDrop ? drop.inv_keep : 1.0f) / l;
-    __nv_bfloat16* orow = out + ((long long)b * N + q) * D + h * kHd;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    __nv_bfloat16* orow = out + ((long long)b * N + q) * D + h * kHd + hf * 32;
+    {
       uint32_t o[32];
-      tmem_ld32(tO + lane_off + c * 32, o);
+      tmem_ld32(tO + lane_off + hf * 32, o);
       tmem_ld_wait();
       if (q < N) {
 #pragma unroll
@@ -233,16 +261,16 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             v[u] = pack_bf16(__uint_as_float(o[16 * t + 2 * u]) * inv, __uint_as_float(o[16 * t + 2 * u + 1]) * inv);
-          st_global_b32x8(orow + c * 32 + 16 * t, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+          st_global_b32x8(orow + 16 * t, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
         }
       }
     }
-    if (q < N) lse[((long long)b * H + h) * N + q] = (m2 + log2f(l)) * 0.69314718055994531f;
+    if (hf == 0 && q < N) lse[((long long)b * H + h) * N + q] = (m2 + log2f(l)) * 0.69314718055994531f;
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
@@ -260,7 +288,7 @@ int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int
   if (hd != kHd) return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 attention supports head_dim 64 only (got %d)", hd);
   const int D = H * hd;
   if (D % 8 != 0) return fail(TVIT_ERR_BAD_ARG, "attention: embed dim must be a multiple of 8");
-  constexpr int smem_bytes = 5 * kTileBytes + 1024 + 256;
+  constexpr int smem_bytes = 5 * kTileBytes + 1024 + 256 + 2048;  // tiles + alignment + barriers + partner exchange
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
