@@ -1,0 +1,67 @@
+"""Shapes of the other BASELINE.json configs at reduced depth/batch (B200 only): the large variant
+(D768/H12), the long-sequence variant (32x128x512 -> N = 16385 tokens) and the full configs[1] token count
+(N = 2049).  The bf16 tensor-core path is compared with the on-device fp32 verification path (itself pinned to
+the reference by the golden-vector and fp64-oracle tests), because the fp64 oracle's O(N^2) score tensors do
+not fit these sizes comfortably."""
+import pytest
+import torch
+
+import neural_vit_b200 as nv
+from oracle import vit_oracle as O
+from tests.conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CASES = [
+    ("large_d768_h12_n513", dict(n_trials=8, freq_size=64, time_size=128, embed_dim=768, n_heads=12, n_layers=2), 2),
+    ("small_n2049", dict(n_trials=8, freq_size=128, time_size=256, embed_dim=384, n_heads=6, n_layers=1), 2),
+    ("longseq_n16385", dict(n_trials=32, freq_size=128, time_size=512, embed_dim=384, n_heads=6, n_layers=1), 1),
+    ("base_d512_h8_n257", dict(n_trials=4, freq_size=64, time_size=128, embed_dim=512, n_heads=8, n_layers=2), 3),
+]
+
+
+@pytest.mark.parametrize("tag,kw,batch", CASES, ids=[c[0] for c in CASES])
+def test_bf16_path_matches_fp32_path(tag, kw, batch):
+    kw = dict(kw, dropout=0.0, attention_dropout=0.0, drop_path=0.0)
+    cfg = nv.Temporal3DViTConfig(**kw)
+    params = O.random_params(O.config_from(cfg), seed=21)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(batch, cfg.n_trials, cfg.freq_size, cfg.time_size, generator=g).to(DEV)
+    y = torch.randint(0, 2, (batch,), generator=g).to(DEV)
+    out = {}
+    for precision in ("fp32", "bf16"):
+        m = nv.Temporal3DViT(cfg, precision=precision)
+        m.load_state_dict(params)
+        m.to(DEV).train()
+        logits = m(x)
+        loss = torch.nn.functional.cross_entropy(logits, y)
+        loss.backward()
+        out[precision] = (logits.detach(), {k: p.grad.detach().clone() for k, p in m.named_parameters()})
+        del m
+    l32, g32 = out["fp32"]
+    l16, g16 = out["bf16"]
+    assert torch.isfinite(l16).all()
+    assert rel_err(l16, l32) < 2e-2
+    flat16 = torch.cat([g16[k].double().flatten() for k in g32])
+    flat32 = torch.cat([g32[k].double().flatten() for k in g32])
+    assert rel_err(flat16, flat32) < 2e-2
+    worst = max((rel_err(g16[k], g32[k]), k) for k in g32 if g32[k].numel() > 4096)
+    assert worst[0] < 3e-2, worst
+
+
+def test_batch_of_one_and_odd_batch():
+    cfg = nv.Temporal3DViTConfig(n_trials=4, freq_size=32, time_size=64, embed_dim=128, n_heads=2, n_layers=1,
+                                 dropout=0.0, attention_dropout=0.0, drop_path=0.0)
+    params = O.random_params(O.config_from(cfg), seed=3)
+    m = nv.Temporal3DViT(cfg)
+    m.load_state_dict(params)
+    m.to(DEV).eval()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(5, 4, 32, 64, generator=g).to(DEV)
+    with torch.no_grad():
+        full = m(x)
+        one = torch.cat([m(x[i:i + 1]) for i in range(5)])
+    assert rel_err(one, full) < 1e-5       # samples are independent (batch-sharded data parallelism relies on it)
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 4, 32, 60, device=DEV))
