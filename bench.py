@@ -111,6 +111,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic_bytes(batch, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/r1_ncu_attn_B256_dropout.json); only valid for the shape it was captured on."""
+    if (batch, args.layers, args.embed_dim, args.trials, args.time) != (256, 8, 384, 8, 256):
+        return None
+    path = os.path.join(ROOT, "profiles", "r1_ncu_attn_B256_dropout.json")
+    try:
+        with open(path) as fh:
+            k = json.load(fh)["void tc_attn_bwd_kernel<1>"]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        return sum(float(k[m][0]) * scale[k[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -182,12 +197,15 @@ def main():
     ap.add_argument("--layers", type=int, default=8)
     ap.add_argument("--embed-dim", type=int, default=384)
     ap.add_argument("--heads", type=int, default=6)
+    ap.add_argument("--trials", type=int, default=8)
+    ap.add_argument("--freq", type=int, default=128)
+    ap.add_argument("--time", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print a per-op time breakdown to stderr")
     args = ap.parse_args()
 
-    cfg_kwargs = dict(n_trials=8, freq_size=128, time_size=256, embed_dim=args.embed_dim, n_heads=args.heads,
-                      n_layers=args.layers)
+    cfg_kwargs = dict(n_trials=args.trials, freq_size=args.freq, time_size=args.time, embed_dim=args.embed_dim,
+                      n_heads=args.heads, n_layers=args.layers)
     if args.dropout is not None:
         cfg_kwargs.update(dropout=args.dropout, attention_dropout=args.dropout, drop_path=args.dropout)
     if args.impl == "reference":
@@ -305,9 +323,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD if (B, args.layers, args.embed_dim, args.dropout) == (256, 8, 384, None)
-                   else f"D{args.embed_dim}/H{args.heads}/L{args.layers}, 8x128x256, batch {B} per GPU, bf16, "
-                        f"dropout {cfg.dropout}",
+        "config": {"workload": WORKLOAD if (B, args.layers, args.embed_dim, args.dropout, args.trials, args.time) ==
+                   (256, 8, 384, None, 8, 256)
+                   else f"D{args.embed_dim}/H{args.heads}/L{args.layers}, {args.trials}x{args.freq}x{args.time}, "
+                        f"batch {B} per GPU, bf16, dropout {cfg.dropout}",
                    "step": "zero_grad + forward + weighted CE + backward" + (" + bucketed NCCL all-reduce" if world > 1 else "")
                            + " + AdamW", "global_batch": world * B, "tokens_per_sample": cfg.n_patches + 1,
                    "parallelism": f"dp{world}", "l2": "per-step working set (>= 268 MB input, tens of GB of activations) exceeds the 126 MB L2"},
@@ -320,7 +339,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "tc_attn_bwd_kernel (+prep/finish)", "achieved": attn_tflops,
                      "peak": sustained, "peak_kind": f"{which} sustained cuBLAS bf16", "unit": "TFLOP/s",
                      "frac": attn_tflops / sustained, "ms_per_launch": attn_ms_avg, "launches_timed": len(attn_ms),
-                     "traffic": None},
+                     "traffic": ncu_traffic_bytes(B, args)},
     }
     if breakdown:
         line["breakdown_ms"] = breakdown
