@@ -94,18 +94,20 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
     // ============================ MMA issuer ============================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B = V: MN-major
-    const uint32_t aQ = smem_u32(sQ);
+    // descriptor low words formed once and stepped by constants (short issue loops: this warp shares its
+    // scheduler with busy softmax warps)
+    constexpr uint32_t kHi = umma_desc_hi(1024);
+    const uint32_t dQ = umma_desc_lo(smem_u32(sQ), 0), dKV0 = umma_desc_lo(smem_u32(sKV), 0);
     mbar_wait(&sm->q_full, 0);
     auto issue_s = [&](int j) {
       const int st = j & 1;
       mbar_wait(&sm->kv_full[st], ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
-      const uint32_t aK = smem_u32(sKV + st * 2 * kTileBytes);
+      const uint32_t dK = dKV0 + (uint32_t)st * (2 * kTileBytes >> 4);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kHd / 16; ++k)
-          umma_ss(tS, umma_smem_desc(aQ + k * 32, 0, 1024), umma_smem_desc(aK + k * 32, 0, 1024), idesc_s,
-                  k > 0 ? 1u : 0u);
+          umma_ss(tS, umma_desc(dQ + 2 * k, kHi), umma_desc(dK + 2 * k, kHi), idesc_s, k > 0 ? 1u : 0u);
         tc_commit(&sm->s_full);
       }
       __syncwarp();
@@ -120,11 +122,11 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
       }
       mbar_wait(&sm->p_full, (uint32_t)j & 1u);  // P_j in TMEM, O rescaled
       tc_fence_after();
-      const uint32_t aV = smem_u32(sKV + st * 2 * kTileBytes + kTileBytes);
+      const uint32_t dVm = (dKV0 + (uint32_t)st * (2 * kTileBytes >> 4) + (kTileBytes >> 4)) | ((16384u >> 4) << 16);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kTile / 16; ++k)
-          umma_ts(tO, tP + k * 8, umma_smem_desc(aV + k * 2048, 16384, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          umma_ts(tO, tP + k * 8, umma_desc(dVm + 128 * k, kHi), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(&sm->kv_empty[st]);
         tc_commit(&sm->pv_done);
       }

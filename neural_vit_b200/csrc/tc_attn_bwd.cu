@@ -13,6 +13,14 @@
 // dedicated warps with coalesced 16-byte fp32 reductions into a tile-chunked accumulator and converted
 // to bf16 by a finishing kernel; dK_j / dV_j stay in TMEM across the whole query loop.
 // D = rowsum(dO o O) and lse are read per query row (one scalar each per thread per tile).
+//
+// Pipelining.  TMEM (512 columns: S 128, dP 128, dV 64, dK 64, dQ 64) has no room for a second S / dP tile, so
+// the tile is pipelined by key halves instead: S and dP are issued as two N = 64 MMA groups (keys [0,64) and
+// [64,128)), every softmax warp processes half a then half b and releases each half's TMEM columns right after
+// its tcgen05.ld, and the MMA warp refills half a of tile i+1 while the softmax warps are still working on half
+// b of tile i.  Q/dO tiles are triple-buffered, dS double-buffered, P single-buffered (dV_i is issued first and
+// frees it long before the first P store of tile i+1).  Each CTA starts its query loop at its own key-tile index
+// (i -> (i + j) mod nq) so that the CTAs of one (sample, head) never reduce into the same dQ tile at once.
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -23,7 +31,7 @@ constexpr int kHdB = 64;
 constexpr int kTileB = 128;
 constexpr int kTileBytesB = kTileB * kHdB * 2;  // 16384: one [128 x 64] bf16 operand tile
 constexpr int kPBytes = kTileB * kTileB * 2;    // 32768: one [128 x 128] bf16 P / dS tile (two 64-wide blocks)
-constexpr int kAttnBwdThreads = 768;  // warps 0-15 softmax, 16 TMA, 17 MMA (+TMEM alloc), 20-23 dQ drain
+constexpr int kAttnBwdThreads = 768;  // warps 0-15 softmax, 16-19 dQ drain, 20 TMA, 21 MMA (+TMEM alloc), 22-23 idle
 constexpr int kSoftmaxWarps = 16;
 
 __host__ __device__ __forceinline__ unsigned long long attn_drop_row_base_b(int b, int H, int h, int N, int q) {
@@ -31,8 +39,10 @@ __host__ __device__ __forceinline__ unsigned long long attn_drop_row_base_b(int 
   return (((unsigned long long)b * H + h) * N + q) * npad;
 }
 
+constexpr int kQStages = 3;  // Q / dO tiles in flight
 struct AttnBwdSmem {
-  uint64_t kv_full, qdo_full[2], qdo_empty[2], s_full, s_free, p_full, mma_done[2], dq_full, dq_free;
+  uint64_t kv_full, qdo_full[kQStages], qdo_empty[kQStages], s_full[2], s_free[2], p_full, p_free, ds_free[2], dq_full,
+      dq_free;
   uint32_t tmem_base;
 };
 
@@ -99,9 +109,10 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;
   uint8_t* sV = smem + kTileBytesB;
-  uint8_t* sQdO = smem + 2 * kTileBytesB;                 // stage s: Q at +s*32K, dO at +s*32K+16K
-  uint8_t* sPDS = smem + 6 * kTileBytesB;  // buffer u (= tile parity): P at +u*64K, dS at +u*64K+32K
-  AttnBwdSmem* sm = reinterpret_cast<AttnBwdSmem*>(sPDS + 4 * kPBytes);
+  uint8_t* sQdO = smem + 2 * kTileBytesB;  // stage s: Q at +s*32K, dO at +s*32K+16K
+  uint8_t* sP = sQdO + kQStages * 2 * kTileBytesB;   // P  [2 key blocks][128 q rows][64 keys], single buffer
+  uint8_t* sDS = sP + kPBytes;                       // dS, same layout, buffer u (= tile parity) at +u*32K
+  AttnBwdSmem* sm = reinterpret_cast<AttnBwdSmem*>(sDS + 2 * kPBytes);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -112,20 +123,22 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   if (threadIdx.x == 0) {
     mbar_init(&sm->kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kQStages; ++i) {
       mbar_init(&sm->qdo_full[i], 1);
       mbar_init(&sm->qdo_empty[i], 1);
     }
-    mbar_init(&sm->s_full, 1);
-    mbar_init(&sm->s_free, kSoftmaxWarps);  // one elected arrive per softmax warp
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm->s_full[i], 1);
+      mbar_init(&sm->s_free[i], kSoftmaxWarps);  // one elected arrive per softmax warp
+      mbar_init(&sm->ds_free[i], 1);
+    }
     mbar_init(&sm->p_full, kSoftmaxWarps);
-    mbar_init(&sm->mma_done[0], 1);
-    mbar_init(&sm->mma_done[1], 1);
+    mbar_init(&sm->p_free, 1);
     mbar_init(&sm->dq_full, 1);
     mbar_init(&sm->dq_free, 128);
     fence_barrier_init();
   }
-  if (warp == 17) {
+  if (warp == 21) {
     tmem_alloc(&sm->tmem_base, 512);
     tmem_relinquish();
   }
@@ -138,7 +151,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   // Role code below is warp-uniform (all 32 lanes run the loops and the barrier waits); only the TMA / MMA /
   // commit instructions themselves are predicated on one elected lane.  Issuing them from divergent code
   // (`if (lane == 0)`) makes ptxas wrap every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST loop (~100 clk each).
-  if (warp == 16) {
+  if (warp == 20) {
     // ============================ TMA producer ============================
     if (elect_one()) {
       tma_prefetch_desc(&tm_qkv);
@@ -149,63 +162,83 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     __syncwarp();
     for (int i = 0; i < nq; ++i) {
-      const int st = i & 1;
-      mbar_wait_backoff(&sm->qdo_empty[st], (((uint32_t)i >> 1) & 1u) ^ 1u);
+      const int st = i % kQStages;
+      const int qt = (i + jt) % nq;  // staggered start, see header
+      mbar_wait_backoff(&sm->qdo_empty[st], (((uint32_t)i / kQStages) & 1u) ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(&sm->qdo_full[st], 2 * kTileBytesB);
         uint8_t* sQ = sQdO + st * 2 * kTileBytesB;
-        tma_load_3d(sQ, &tm_qkv, &sm->qdo_full[st], h * kHdB, i * kTileB, b);
-        tma_load_3d(sQ + kTileBytesB, &tm_do, &sm->qdo_full[st], h * kHdB, i * kTileB, b);
+        tma_load_3d(sQ, &tm_qkv, &sm->qdo_full[st], h * kHdB, qt * kTileB, b);
+        tma_load_3d(sQ + kTileBytesB, &tm_do, &sm->qdo_full[st], h * kHdB, qt * kTileB, b);
       }
       __syncwarp();
     }
-  } else if (warp == 17) {
+  } else if (warp == 21) {
     // ============================ MMA issuer ============================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP: both operands K-major
+    constexpr uint32_t idesc_h = umma_idesc_bf16(128, 64, 0, 0);    // S, dP halves: both operands K-major
     constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);    // dV, dK: A (sP/sDS) MN-major, B MN-major
     constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);    // dQ: A (sDS) K-major, B (K_j) MN-major
-    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-    mbar_wait(&sm->kv_full, 0);
-    auto issue_sdp = [&](int i) {
-      const int st = i & 1;
-      mbar_wait(&sm->qdo_full[st], ((uint32_t)i >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t aQ = smem_u32(sQdO + st * 2 * kTileBytesB), aDO = aQ + kTileBytesB;
+    // Descriptor low words (start >> 4 | LBO field) are formed once per tile and stepped by constants, and the high
+    // word is a compile-time constant: the issue loops must stay short because this warp competes for issue slots
+    // with four busy softmax warps on its scheduler.
+    constexpr uint32_t kHi = umma_desc_hi(1024);
+    constexpr uint32_t kMn = (16384u >> 4) << 16;                 // LBO of the MN-major [2 x 64] tiles
+    const uint32_t dK = umma_desc_lo(smem_u32(sK), 0), dV = umma_desc_lo(smem_u32(sV), 0);
+    const uint32_t dQ0 = umma_desc_lo(smem_u32(sQdO), 0), dP = umma_desc_lo(smem_u32(sP), 0) | kMn;
+    const uint32_t dDS0 = umma_desc_lo(smem_u32(sDS), 0);
+    // S / dP of a tile for the keys [64 hf, 64 hf + 64): rows [64 hf, ..) of the K-major K_j / V_j tiles
+    auto issue_half = [&](int st, int hf) {
+      const uint32_t dQ = dQ0 + (uint32_t)st * (2 * kTileBytesB >> 4), dDO = dQ + (kTileBytesB >> 4);
+      const uint32_t dKh = dK + (uint32_t)hf * (kTileBytesB / 2 >> 4), dVh = dV + (uint32_t)hf * (kTileBytesB / 2 >> 4);
       if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kHdB / 16; ++k)
-            umma_ss(tS, umma_smem_desc(aQ + k * 32, 0, 1024), umma_smem_desc(aK + k * 32, 0, 1024), idesc_s,
-                    k > 0 ? 1u : 0u);
+        for (int k = 0; k < kHdB / 16; ++k)
+          umma_ss(tS + hf * 64, umma_desc(dQ + 2 * k, kHi), umma_desc(dKh + 2 * k, kHi), idesc_h, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < kHdB / 16; ++k)
-            umma_ss(tDP, umma_smem_desc(aDO + k * 32, 0, 1024), umma_smem_desc(aV + k * 32, 0, 1024), idesc_s,
-                    k > 0 ? 1u : 0u);
-        tc_commit(&sm->s_full);
+        for (int k = 0; k < kHdB / 16; ++k)
+          umma_ss(tDP + hf * 64, umma_desc(dDO + 2 * k, kHi), umma_desc(dVh + 2 * k, kHi), idesc_h, k > 0 ? 1u : 0u);
+        tc_commit(&sm->s_full[hf]);
       }
       __syncwarp();
     };
-    issue_sdp(0);
+    mbar_wait(&sm->kv_full, 0);
+    mbar_wait(&sm->qdo_full[0], 0);
+    tc_fence_after();
+    issue_half(0, 0);
+    issue_half(0, 1);
+    int st = 0;
     for (int i = 0; i < nq; ++i) {
-      const int st = i & 1;
-      if (i + 1 < nq) {
-        mbar_wait(&sm->s_free, (uint32_t)i & 1u);  // softmax_i has consumed tS / tDP
+      const int stn = st + 1 == kQStages ? 0 : st + 1;
+      const bool more = i + 1 < nq;
+      if (more) {  // refill half a while the softmax warps work on half b of tile i
+        mbar_wait(&sm->qdo_full[stn], ((uint32_t)(i + 1) / kQStages) & 1u);
+        mbar_wait(&sm->s_free[0], (uint32_t)i & 1u);
         tc_fence_after();
-        issue_sdp(i + 1);
+        issue_half(stn, 0);
       }
       mbar_wait(&sm->p_full, (uint32_t)i & 1u);  // sP / sDS written for tile i
       tc_fence_after();
-      const uint32_t aQ = smem_u32(sQdO + st * 2 * kTileBytesB), aDO = aQ + kTileBytesB;
-      const uint32_t aP = smem_u32(sPDS + st * 2 * kPBytes), aDS = aP + kPBytes;
+      // MN-major operands (LBO 16384): Q_i, dO_i as B; sP, sDS as A.  K-major sDS as A of the dQ MMA.
+      const uint32_t dQm = (dQ0 + (uint32_t)st * (2 * kTileBytesB >> 4)) | kMn, dDOm = dQm + (kTileBytesB >> 4);
+      const uint32_t dDS = dDS0 + (uint32_t)(i & 1) * (kPBytes >> 4), dDSm = dDS | kMn, dKm = dK | kMn;
+      const uint32_t accum = i > 0 ? 1u : 0u;
       if (elect_one()) {
-          // reduction over the 128 query rows in 8 steps of 16 (2048 B per step in the MN-major tiles)
+        // reduction over the 128 query rows in 8 steps of 16 (2048 B per step in the MN-major tiles)
 #pragma unroll
-          for (int k = 0; k < kTileB / 16; ++k)
-            umma_ss(tDV, umma_smem_desc(aP + k * 2048, 16384, 1024), umma_smem_desc(aDO + k * 2048, 16384, 1024),
-                    idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < kTileB / 16; ++k)
+          umma_ss(tDV, umma_desc(dP + 128 * k, kHi), umma_desc(dDOm + 128 * k, kHi), idesc_t, k > 0 ? 1u : accum);
+        tc_commit(&sm->p_free);  // sP may be overwritten by tile i+1
+      }
+      __syncwarp();
+      if (more) {
+        mbar_wait(&sm->s_free[1], (uint32_t)i & 1u);
+        tc_fence_after();
+        issue_half(stn, 1);
+      }
+      if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kTileB / 16; ++k)
-            umma_ss(tDK, umma_smem_desc(aDS + k * 2048, 16384, 1024), umma_smem_desc(aQ + k * 2048, 16384, 1024),
-                    idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < kTileB / 16; ++k)
+          umma_ss(tDK, umma_desc(dDSm + 128 * k, kHi), umma_desc(dQm + 128 * k, kHi), idesc_t, k > 0 ? 1u : accum);
       }
       __syncwarp();
       if (i > 0) {
@@ -215,48 +248,55 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       if (elect_one()) {
         // reduction over the 128 keys: sDS K-major (two 64-key blocks 16 KB apart), K_j MN-major
 #pragma unroll
-          for (int k = 0; k < kTileB / 16; ++k)
-            umma_ss(tDQ, umma_smem_desc(aDS + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024),
-                    umma_smem_desc(aK + k * 2048, 16384, 1024), idesc_q, k > 0 ? 1u : 0u);
+        for (int k = 0; k < kTileB / 16; ++k)
+          umma_ss(tDQ, umma_desc(dDS + (k >> 2) * (16384 >> 4) + (k & 3) * 2, kHi), umma_desc(dKm + 128 * k, kHi),
+                  idesc_q, k > 0 ? 1u : 0u);
         tc_commit(&sm->qdo_empty[st]);
         tc_commit(&sm->dq_full);
-        tc_commit(&sm->mma_done[st]);
+        tc_commit(&sm->ds_free[i & 1]);
       }
       __syncwarp();
+      st = stn;
     }
   } else if (warp < kSoftmaxWarps) {
-    // ============ softmax warps: thread == query row (TMEM lane quarter warp % 4), key half warp / 4 ============
-    const int qd4 = warp & 3, chunk = warp >> 2;  // 32 query rows x 32 keys per warp per tile
+    // ===== softmax warps: thread == query row (TMEM lane quarter warp % 4), 16 keys (warp / 4) of each key half =====
+    const int qd4 = warp & 3, chunk = warp >> 2;
     const int r = qd4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd4 * 32) << 16;
     const float c_log2 = scale * 1.4426950408889634f;
     const float* lse_bh = lse + ((long long)b * H + h) * N;
     const float* dv_bh = dvec + ((long long)b * H + h) * N;
-    float lse_next = (r < N) ? lse_bh[r] : INFINITY, d_next = (r < N) ? dv_bh[r] : 0.f;
+    int qt = jt % nq;
+    float lse_next = (qt * kTileB + r < N) ? lse_bh[qt * kTileB + r] : INFINITY;
+    float d_next = (qt * kTileB + r < N) ? dv_bh[qt * kTileB + r] : 0.f;
     for (int i = 0; i < nq; ++i) {
-      const int q = i * kTileB + r;
+      const int q = qt * kTileB + r;
       const float lse2 = lse_next * 1.4426950408889634f;  // +inf for rows past N -> P = 0
       const float Dq = d_next * scale;  // dS = P * (dP * scale - D * scale)
       {  // prefetch the next tile's row statistics so the global-load latency is off the critical path
-        const int qn = q + kTileB;
+        qt = (qt + 1 == nq) ? 0 : qt + 1;
+        const int qn = qt * kTileB + r;
         lse_next = (qn < N) ? lse_bh[qn] : INFINITY;
         d_next = (qn < N) ? dv_bh[qn] : 0.f;
       }
-      const uint32_t aPbuf = smem_u32(sPDS) + (uint32_t)(i & 1) * 2u * kPBytes;  // P buffer; dS follows at +32K
+      const uint32_t aDSbuf = smem_u32(sDS) + (uint32_t)(i & 1) * kPBytes;
       const unsigned long long rowe = attn_drop_row_base_b(b, H, h, N, q < N ? q : 0) + (unsigned long long)kv0;
-      mbar_wait(&sm->s_full, (uint32_t)i & 1u);
-      tc_fence_after();
 #pragma unroll 1
-      for (int sc = 0; sc < 2; ++sc) {  // two 16-key sub-chunks keep the live register set small (16 warps / SM)
+      for (int hf = 0; hf < 2; ++hf) {  // key halves; 16 keys per thread per half keep the live register set small
         uint32_t sv[16], dp[16];
-        tmem_ld16(tS + lane_off + chunk * 32 + sc * 16, sv);
-        tmem_ld16(tDP + lane_off + chunk * 32 + sc * 16, dp);
+        mbar_wait(&sm->s_full[hf], (uint32_t)i & 1u);
+        tc_fence_after();
+        tmem_ld16(tS + lane_off + hf * 64 + chunk * 16, sv);
+        tmem_ld16(tDP + lane_off + hf * 64 + chunk * 16, dp);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->s_free[hf]);  // this half's S / dP columns may be refilled
         uint32_t pk[8], dk[8];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           uint32_t w[4] = {0, 0, 0, 0};
-          if (kDrop) drop_bits8(drop, (rowe >> 3) + (unsigned long long)(chunk * 4 + sc * 2 + g), w);
+          if (kDrop) drop_bits8(drop, (rowe >> 3) + (unsigned long long)(hf * 8 + chunk * 2 + g), w);
 #pragma unroll
           for (int t = 0; t < 8; t += 2) {
             float p0 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_log2, -lse2));
@@ -277,28 +317,25 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             pk[g * 4 + (t >> 1)] = pack_bf16(p0, p1);
           }
         }
-        if (sc == 0 && i >= 2) {  // the MMAs of tile i-2 have finished reading this P / dS buffer
-          mbar_wait(&sm->mma_done[i & 1], (((uint32_t)i >> 1) - 1u) & 1u);
+        if (hf == 0) {
+          if (i >= 1) mbar_wait(&sm->p_free, (uint32_t)(i - 1) & 1u);  // dV_{i-1} has read sP
+          if (i >= 2) mbar_wait(&sm->ds_free[i & 1], (((uint32_t)i >> 1) - 1u) & 1u);  // tile i-2 has read this sDS
         }
-        // row r of 64-key block (chunk >> 1): 16-byte pieces (chunk & 1) * 4 + sc * 2 + g, XOR-swizzled with (r & 7)
-        const uint32_t row_off = (uint32_t)(chunk >> 1) * 16384u + (uint32_t)r * 128u;
+        // row r of 64-key block hf: 16-byte pieces chunk * 2 + g, XOR-swizzled with (r & 7)
+        const uint32_t row_off = (uint32_t)hf * 16384u + (uint32_t)r * 128u;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const uint32_t piece = (uint32_t)(((chunk & 1) * 4 + sc * 2 + g) ^ (r & 7)) * 16u;
-          st_shared_v4(aPbuf + row_off + piece, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          st_shared_v4(aPbuf + kPBytes + row_off + piece, dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+          const uint32_t piece = (uint32_t)((chunk * 2 + g) ^ (r & 7)) * 16u;
+          st_shared_v4(smem_u32(sP) + row_off + piece, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          st_shared_v4(aDSbuf + row_off + piece, dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
         }
       }
-      tc_fence_before();
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&sm->s_free);
-        mbar_arrive(&sm->p_full);
-      }
+      if (lane == 0) mbar_arrive(&sm->p_full);
     }
     // ---- epilogue: dK_j, dV_j from TMEM -> bf16 rows of dqkv ----
-    mbar_wait(&sm->mma_done[(nq - 1) & 1], ((uint32_t)(nq - 1) >> 1) & 1u);
+    mbar_wait(&sm->ds_free[(nq - 1) & 1], ((uint32_t)(nq - 1) >> 1) & 1u);
     tc_fence_after();
     const int kv = kv0 + r;
     __nv_bfloat16* drow = dqkv + ((long long)b * N + kv) * (3LL * D) + h * kHdB;
@@ -319,8 +356,8 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         }
       }
     }
-  } else if (warp >= 20) {
-    // ============================ dQ drain warps ============================
+  } else if (warp < 20) {
+    // ============================ dQ drain warps (16-19) ============================
     const int qd = warp & 3;  // TMEM lane quarter (warp % 4)
     const int r = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
@@ -328,31 +365,29 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     for (int i = 0; i < nq; ++i) {
       mbar_wait_backoff(&sm->dq_full, (uint32_t)i & 1u);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld32(tDQ + lane_off, o0);
-      tmem_ld32(tDQ + lane_off + 32, o1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&sm->dq_free);
-      float* tile = acc_bh + (long long)i * (16 * 128 * 4) + r * 4;
+      float* tile = acc_bh + (long long)((i + jt) % nq) * (16 * 128 * 4) + r * 4;
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {  // 32 columns at a time: this warpgroup runs with 64 registers
+        uint32_t o[32];
+        tmem_ld32(tDQ + lane_off + hc * 32, o);
+        tmem_ld_wait();
+        if (hc == 1) {
+          tc_fence_before();
+          mbar_arrive(&sm->dq_free);
+        }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        atomicAdd(reinterpret_cast<float4*>(tile + c * 512),
-                  make_float4(__uint_as_float(o0[4 * c]), __uint_as_float(o0[4 * c + 1]), __uint_as_float(o0[4 * c + 2]),
-                              __uint_as_float(o0[4 * c + 3])));
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        atomicAdd(reinterpret_cast<float4*>(tile + (8 + c) * 512),
-                  make_float4(__uint_as_float(o1[4 * c]), __uint_as_float(o1[4 * c + 1]), __uint_as_float(o1[4 * c + 2]),
-                              __uint_as_float(o1[4 * c + 3])));
+        for (int c = 0; c < 8; ++c) {
+          atomicAdd(reinterpret_cast<float4*>(tile + (hc * 8 + c) * 512),
+                    make_float4(__uint_as_float(o[4 * c]), __uint_as_float(o[4 * c + 1]), __uint_as_float(o[4 * c + 2]),
+                                __uint_as_float(o[4 * c + 3])));
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) {
+  if (warp == 21) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -386,7 +421,7 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   float* dqacc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + ws_dvec_bytes(B, N, H));
   const size_t dq_bytes = (size_t)B * H * nq * 16 * 128 * 4 * sizeof(float);
 
-  constexpr int smem_bytes = 2 * kTileBytesB + 4 * kTileBytesB + 4 * kPBytes + 1024 + 256;  // 225.25 KB
+  constexpr int smem_bytes = 2 * kTileBytesB + kQStages * 2 * kTileBytesB + 3 * kPBytes + 1024 + 256;  // 225.25 KB
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {

@@ -282,6 +282,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same descriptor split into its 32-bit halves, for issue loops that keep a per-tile base in a register and
+// add byte offsets: lo = start >> 4 | (LBO >> 4) << 16 (tiles live below 256 KB, so adding (offset >> 4) to lo
+// never carries into the LBO field), hi = SBO >> 4 | version | swizzle mode.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulate.
 //   [4,6) D fmt: 1 = f32   [7,10) A fmt: 1 = bf16   [10,13) B fmt: 1 = bf16
 //   [15] A major (0 = K, 1 = MN)   [16] B major   [17,23) N >> 3   [24,29) M >> 4

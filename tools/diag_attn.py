@@ -76,6 +76,12 @@ def main():
                 if errs[i] > 3e-2:
                     d = (got[:, i].double() - gq[:, i]).abs().reshape(B, N, H, hd)
                     print(f"  d{nm} err by row block:", [f"{d[0, r:r + 32, 0].max().item():.2e}" for r in range(0, min(N, 256), 32)])
+    # box calibration: cuBLAS bf16 GEMM (boxes differ by a few % in sustained clocks)
+    a = torch.randn(8192, 8192, device=DEV).bfloat16()
+    bb = torch.randn(8192, 8192, device=DEV).bfloat16()
+    t = timeit(lambda: torch.matmul(a, bb), iters=20)
+    print(f"calibration cuBLAS 8192^3 bf16: {2 * 8192**3 / t / 1e9:.0f} TFLOP/s", flush=True)
+    del a, bb
     # timing at the C2 shape
     B, N, H = 256, 2049, 6
     D = H * hd
@@ -92,6 +98,8 @@ def main():
         dqkv = torch.empty_like(qkv)
         t = timeit(lambda: ops.attn_bwd(L.ENGINE_TCGEN05, L.BF16, qkv, out, dout, lse, dqkv, B, N, H, hd))
         print(f"bwd C2 shape: {t:.3f} ms  {2.5 * fl / t / 1e9:.0f} TFLOP/s", flush=True)
+        t = timeit(lambda: ops.attn_bwd(L.ENGINE_TCGEN05, L.BF16, qkv, out, dout, lse, dqkv, B, N, H, hd, (1, 2, 0.1)))
+        print(f"bwd C2 shape dropout 0.1: {t:.3f} ms  {2.5 * fl / t / 1e9:.0f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":

@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/diag_attn.py --bwd 2>&1 | grep -v Warn | tail -n 6
+timeout 600 python tools/diag_attn.py --bwd 2>&1 | grep -v Warn | tail -n 9
