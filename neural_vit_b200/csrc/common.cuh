@@ -207,4 +207,40 @@ __device__ __forceinline__ float drop_mult(const DropCfg& c, unsigned long long 
   return bits >= c.thr16 ? c.inv_keep : 0.0f;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Attention-probability dropout (the N x N site): 16 elements per Philox call, 8 random bits per element.
+// An 8-bit compare alone would quantise p to 1/256, so the threshold of each 16-element group is dithered:
+//   T_g = (thr16 >> 8) + [weyl8(g, seed) < (thr16 & 255)],   keep(e) <=> byte(e) >= T_g,
+// where weyl8 is the top byte of a golden-ratio Weyl sequence over the group index.  With the dither counted as
+// part of the generator, every element is dropped with probability exactly thr16 / 65536 (the same marginal as the
+// 16-bit scheme used by the GEMM epilogues); elements of one group share T_g, a correlation of ~4e-5.
+// Element index: row-major over (b, h, q, k) with the k extent padded to a multiple of 16 so that groups never
+// straddle rows; forward, backward and the SIMT verification path all use these helpers.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long attn_drop_row_base(int b, int H, int h, int N, int q) {
+  const unsigned long long npad = (unsigned long long)((N + 15) & ~15);
+  return (((unsigned long long)b * H + h) * N + q) * npad;
+}
+__device__ __forceinline__ uint32_t attn_drop_thr8(const DropCfg& c, unsigned long long group16) {
+  const uint32_t weyl = ((uint32_t)group16 * 0x9E3779B1u + (uint32_t)c.seed) >> 24;
+  return (c.thr16 >> 8) + (weyl < (c.thr16 & 255u) ? 1u : 0u);
+}
+// random bytes for the 16 consecutive elements [16 g, 16 g + 16): element j is byte (j & 3) of word j >> 2
+__device__ __forceinline__ void attn_drop_bits16(const DropCfg& c, unsigned long long group16, uint32_t out[4]) {
+  uint4 r = philox4x32_7(c.seed, group16, c.site);
+  out[0] = r.x;
+  out[1] = r.y;
+  out[2] = r.z;
+  out[3] = r.w;
+}
+// keep flag of a single element (SIMT verification path)
+__device__ __forceinline__ bool attn_drop_keep(const DropCfg& c, unsigned long long e) {
+  if (c.thr16 == 0) return true;
+  uint32_t w[4];
+  attn_drop_bits16(c, e >> 4, w);
+  const unsigned int j = (unsigned int)(e & 15ull), k = j >> 2;
+  const uint32_t ww = k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3]));
+  return ((ww >> ((j & 3u) * 8u)) & 0xffu) >= attn_drop_thr8(c, e >> 4);
+}
+
 }  // namespace tvit

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) simt_attn_fwd_kernel(const T* __restrict_
     o[j] = 0.f;
   }
   float mx = -INFINITY, l = 0.f;
-  const unsigned long long rowe = (((unsigned long long)b * H + h) * N + q) * (unsigned long long)((N + 7) & ~7);
+  const unsigned long long rowe = attn_drop_row_base(b, H, h, N, q);
   for (int k = 0; k < N; ++k) {
     const T* kr = base + (long long)k * 3 * D + D + h * hd;
     const T* vr = base + (long long)k * 3 * D + 2 * D + h * hd;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) simt_attn_fwd_kernel(const T* __restrict_
     const float corr = __expf(mx - mn);
     const float p = __expf(s - mn);
     l = l * corr + p;
-    const float pm = p * drop_mult(drop, rowe + k);
+    const float pm = attn_drop_keep(drop, rowe + k) ? p * drop.inv_keep : 0.f;
 #pragma unroll
     for (int j = 0; j < HPL; ++j) o[j] = o[j] * corr + pm * Act<T>::ld(vr + lane + 32 * j);
     mx = mn;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128) simt_attn_bwd_kernel(const T* __restrict_
   }
   dsum = warp_sum(dsum);
   const float L = lse[((long long)b * H + h) * N + q];
-  const unsigned long long rowe = (((unsigned long long)b * H + h) * N + q) * (unsigned long long)((N + 7) & ~7);
+  const unsigned long long rowe = attn_drop_row_base(b, H, h, N, q);
   for (int k = 0; k < N; ++k) {
     const T* kr = base + (long long)k * 3 * D + D + h * hd;
     const T* vr = base + (long long)k * 3 * D + 2 * D + h * hd;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128) simt_attn_bwd_kernel(const T* __restrict_
     s = warp_sum(s) * scale;
     dpd = warp_sum(dpd);
     const float p = __expf(s - L);
-    const float mlt = drop_mult(drop, rowe + k);
+    const float mlt = attn_drop_keep(drop, rowe + k) ? drop.inv_keep : 0.f;
     const float ds = p * (dpd * mlt - dsum) * scale;
     const float pd = p * mlt;
 #pragma unroll

@@ -18,13 +18,6 @@ constexpr int kTile = 128;
 constexpr int kAttnFwdThreads = 320;  // warps 0-7 softmax (2 threads per query row), 8 TMA, 9 MMA
 constexpr int kTileBytes = kTile * kHd * 2;  // 16384
 
-// attention-dropout element index: row-major over (b, h, q, k) with the k extent padded to a multiple of 8
-// so that a thread's 128 consecutive keys start on a Philox group boundary (same definition in simt.cu)
-__host__ __device__ __forceinline__ unsigned long long attn_drop_row_base(int b, int H, int h, int N, int q) {
-  const unsigned long long npad = (unsigned long long)((N + 7) & ~7);
-  return (((unsigned long long)b * H + h) * N + q) * npad;
-}
-
 struct AttnFwdSmem {
   uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, pv_done;
   uint32_t tmem_base;
@@ -146,7 +139,6 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
     const int q = q0 + r;
     float m2 = -INFINITY, l = 0.f;
     const unsigned long long rowe = attn_drop_row_base(b, H, h, N, q < N ? q : 0);
-    const uint32_t thr_hi = drop.thr16 << 16;
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&sm->s_full, (uint32_t)j & 1u);
       tc_fence_after();
@@ -196,7 +188,7 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
       // ---- pass B: exponentials, partial row sum (of the un-dropped probabilities), dropout mask, bf16 pack ----
       // (the 1/(1-p) factor of kept elements is applied once to O in the epilogue)
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-      const unsigned long long g0 = (rowe + (unsigned long long)j * kTile + hf * 64) >> 3;
+      const unsigned long long g0 = (rowe + (unsigned long long)j * kTile + hf * 64) >> 4;  // 16-element groups
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
         uint32_t sv[32];
@@ -214,25 +206,27 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
         }
         uint32_t pk[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w[4] = {0, 0, 0, 0};
-          if (kDrop) drop_bits8(drop, g0 + c2 * 4 + g, w);
+        for (int g = 0; g < 2; ++g) {  // one Philox call per 16 keys (common.cuh: attention-probability dropout)
+          uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0;
+          if (kDrop) {
+            attn_drop_bits16(drop, g0 + c2 * 2 + g, w);
+            tg2 = attn_drop_thr8(drop, g0 + c2 * 2 + g) * 0x10001u;
+          }
 #pragma unroll
-          for (int t = 0; t < 8; t += 4) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), scale_log2, -m_new));
-            float p1 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t + 1]), scale_log2, -m_new));
-            float p2 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t + 2]), scale_log2, -m_new));
-            float p3 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t + 3]), scale_log2, -m_new));
+          for (int u = 0; u < 4; ++u) {
+            const int c = g * 16 + u * 4;
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c]), scale_log2, -m_new));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c + 1]), scale_log2, -m_new));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(sv[c + 2]), scale_log2, -m_new));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(sv[c + 3]), scale_log2, -m_new));
             rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-            if (kDrop) {  // 16 random bits per element: low half via (w << 16), high half via w itself
-              const uint32_t wa = w[t >> 1], wb = w[(t >> 1) + 1];
-              p0 = ((wa << 16) >= thr_hi) ? p0 : 0.f;
-              p1 = (wa >= thr_hi) ? p1 : 0.f;
-              p2 = ((wb << 16) >= thr_hi) ? p2 : 0.f;
-              p3 = (wb >= thr_hi) ? p3 : 0.f;
+            uint32_t v01 = pack_bf16(p0, p1), v23 = pack_bf16(p2, p3);
+            if (kDrop) {
+              v01 &= attn_keep_mask2(w[u], 0, tg2);
+              v23 &= attn_keep_mask2(w[u], 1, tg2);
             }
-            pk[g * 4 + (t >> 1)] = pack_bf16(p0, p1);
-            pk[g * 4 + (t >> 1) + 1] = pack_bf16(p2, p3);
+            pk[g * 8 + u * 2] = v01;
+            pk[g * 8 + u * 2 + 1] = v23;
           }
         }
         tmem_st16(tP + lane_off + hf * 32 + c2 * 16, pk);

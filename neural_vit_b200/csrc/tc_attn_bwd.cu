@@ -34,11 +34,6 @@ constexpr int kPBytes = kTileB * kTileB * 2;    // 32768: one [128 x 128] bf16 P
 constexpr int kAttnBwdThreads = 768;  // warps 0-15 softmax, 16-19 dQ drain, 20 TMA, 21 MMA (+TMEM alloc), 22-23 idle
 constexpr int kSoftmaxWarps = 16;
 
-__host__ __device__ __forceinline__ unsigned long long attn_drop_row_base_b(int b, int H, int h, int N, int q) {
-  const unsigned long long npad = (unsigned long long)((N + 7) & ~7);
-  return (((unsigned long long)b * H + h) * N + q) * npad;
-}
-
 constexpr int kQStages = 3;  // Q / dO tiles in flight
 struct AttnBwdSmem {
   uint64_t kv_full, qdo_full[kQStages], qdo_empty[kQStages], s_full[2], s_free[2], p_full, p_free, ds_free[2], dq_full,
@@ -266,13 +261,16 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const float c_log2 = scale * 1.4426950408889634f;
     const float* lse_bh = lse + ((long long)b * H + h) * N;
     const float* dv_bh = dvec + ((long long)b * H + h) * N;
+    const float log2_inv_keep = kDrop ? __log2f(drop.inv_keep) : 0.f, keep_prob = kDrop ? 1.0f / drop.inv_keep : 1.0f;
     int qt = jt % nq;
     float lse_next = (qt * kTileB + r < N) ? lse_bh[qt * kTileB + r] : INFINITY;
     float d_next = (qt * kTileB + r < N) ? dv_bh[qt * kTileB + r] : 0.f;
     for (int i = 0; i < nq; ++i) {
       const int q = qt * kTileB + r;
-      const float lse2 = lse_next * 1.4426950408889634f;  // +inf for rows past N -> P = 0
-      const float Dq = d_next * scale;  // dS = P * (dP * scale - D * scale)
+      // With dropout (keep mask k, m = k / (1-p)): P m = P' k and dS = P (m dP scale - D scale) = P' (k dP scale - D'),
+      // where P' = P / (1-p) comes for free from the exponent and D' = D scale (1-p).
+      const float lse2 = lse_next * 1.4426950408889634f - log2_inv_keep;  // +inf for rows past N -> P = 0
+      const float negDq = -d_next * scale * keep_prob;
       {  // prefetch the next tile's row statistics so the global-load latency is off the critical path
         qt = (qt + 1 == nq) ? 0 : qt + 1;
         const int qn = qt * kTileB + r;
@@ -280,7 +278,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         d_next = (qn < N) ? dv_bh[qn] : 0.f;
       }
       const uint32_t aDSbuf = smem_u32(sDS) + (uint32_t)(i & 1) * kPBytes;
-      const unsigned long long rowe = attn_drop_row_base_b(b, H, h, N, q < N ? q : 0) + (unsigned long long)kv0;
+      const unsigned long long rowe = attn_drop_row_base(b, H, h, N, q < N ? q : 0) + (unsigned long long)kv0;
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {  // key halves; 16 keys per thread per half keep the live register set small
         uint32_t sv[16], dp[16];
@@ -293,28 +291,26 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm->s_free[hf]);  // this half's S / dP columns may be refilled
         uint32_t pk[8], dk[8];
+        uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0;
+        if (kDrop) {  // this thread's 16 keys are exactly one Philox group (common.cuh)
+          const unsigned long long grp = (rowe >> 4) + (unsigned long long)(hf * 4 + chunk);
+          attn_drop_bits16(drop, grp, w);
+          tg2 = attn_drop_thr8(drop, grp) * 0x10001u;
+        }
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint32_t w[4] = {0, 0, 0, 0};
-          if (kDrop) drop_bits8(drop, (rowe >> 3) + (unsigned long long)(hf * 8 + chunk * 2 + g), w);
-#pragma unroll
-          for (int t = 0; t < 8; t += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_log2, -lse2));
-            float p1 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t + 1]), c_log2, -lse2));
-            float d0 = __uint_as_float(dp[g * 8 + t]), d1 = __uint_as_float(dp[g * 8 + t + 1]);
-            if (kDrop) {
-              const uint32_t b0 = w[t >> 1] & 0xffffu, b1 = w[t >> 1] >> 16;
-              const float m0 = b0 >= drop.thr16 ? drop.inv_keep : 0.f, m1 = b1 >= drop.thr16 ? drop.inv_keep : 0.f;
-              d0 *= m0;
-              d1 *= m1;
-              const float s0 = p0 * fmaf(d0, scale, -Dq), s1 = p1 * fmaf(d1, scale, -Dq);
-              p0 *= m0;
-              p1 *= m1;
-              dk[g * 4 + (t >> 1)] = pack_bf16(s0, s1);
-            } else {
-              dk[g * 4 + (t >> 1)] = pack_bf16(p0 * fmaf(d0, scale, -Dq), p1 * fmaf(d1, scale, -Dq));
-            }
-            pk[g * 4 + (t >> 1)] = pack_bf16(p0, p1);
+        for (int t = 0; t < 8; ++t) {  // element pairs (2t, 2t+1)
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * t]), c_log2, -lse2));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * t + 1]), c_log2, -lse2));
+          const float a0 = fmaf(__uint_as_float(dp[2 * t]), scale, negDq);
+          const float a1 = fmaf(__uint_as_float(dp[2 * t + 1]), scale, negDq);
+          if (kDrop) {
+            const uint32_t m = attn_keep_mask2(w[t >> 1], t & 1, tg2);
+            const uint32_t kept = pack_bf16(p0 * a0, p1 * a1), dropped = pack_bf16(p0 * negDq, p1 * negDq);
+            pk[t] = pack_bf16(p0, p1) & m;
+            dk[t] = (kept & m) | (dropped & ~m);
+          } else {
+            pk[t] = pack_bf16(p0, p1);
+            dk[t] = pack_bf16(p0 * a0, p1 * a1);
           }
         }
         if (hf == 0) {
