@@ -151,12 +151,19 @@ struct DropCfg {
   unsigned int site;   // unique per dropout call site within one forward
   unsigned int thr16;  // 0 => dropout disabled (identity)
   float inv_keep;      // 1 / (1 - p)
+  // Philox round keys (k0 + r W0, k1 + r W1), r = 0..6, filled on the host: the struct is a kernel parameter,
+  // so the rounds read them as constant-bank operands instead of recomputing the key schedule per call
+  unsigned int rk0[7], rk1[7];
 };
 
 __host__ __device__ __forceinline__ DropCfg make_drop(const tvit_dropout* d) {
   DropCfg c;
   c.seed = d ? d->seed : 0ull;
   c.site = d ? d->site : 0u;
+  for (int r = 0; r < 7; ++r) {
+    c.rk0[r] = (unsigned int)c.seed + (unsigned int)r * 0x9E3779B9u;
+    c.rk1[r] = (unsigned int)(c.seed >> 32) + (unsigned int)r * 0xBB67AE85u;
+  }
   float p = d ? d->p : 0.f;
   if (p <= 0.f) {
     c.thr16 = 0;
@@ -187,9 +194,24 @@ __device__ __forceinline__ uint4 philox4x32_7(unsigned long long seed, unsigned 
   return make_uint4(c0, c1, c2, c3);
 }
 
+// same generator with the host-precomputed round keys of a DropCfg kernel parameter
+__device__ __forceinline__ uint4 philox4x32_7(const DropCfg& c, unsigned long long ctr) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = c.site, c3 = 0x5eed5eedu;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ c.rk0[r];
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ c.rk1[r];
+    c3 = lo0;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
 // random 16-bit lanes for the 8 consecutive elements [8*g, 8*g+8)
 __device__ __forceinline__ void drop_bits8(const DropCfg& c, unsigned long long group, uint32_t out[4]) {
-  uint4 r = philox4x32_7(c.seed, group, c.site);
+  uint4 r = philox4x32_7(c, group);
   out[0] = r.x;
   out[1] = r.y;
   out[2] = r.z;
@@ -227,7 +249,7 @@ __device__ __forceinline__ uint32_t attn_drop_thr8(const DropCfg& c, unsigned lo
 }
 // random bytes for the 16 consecutive elements [16 g, 16 g + 16): element j is byte (j & 3) of word j >> 2
 __device__ __forceinline__ void attn_drop_bits16(const DropCfg& c, unsigned long long group16, uint32_t out[4]) {
-  uint4 r = philox4x32_7(c.seed, group16, c.site);
+  uint4 r = philox4x32_7(c, group16);
   out[0] = r.x;
   out[1] = r.y;
   out[2] = r.z;

@@ -285,6 +285,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
 // The same descriptor split into its 32-bit halves, for issue loops that keep a per-tile base in a register and
 // add byte offsets: lo = start >> 4 | (LBO >> 4) << 16 (tiles live below 256 KB, so adding (offset >> 4) to lo
 // never carries into the LBO field), hi = SBO >> 4 | version | swizzle mode.
+// L2 prefetch of the 128-byte line that holds gptr
+__device__ __forceinline__ void l2_prefetch_line(const void* gptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr));
+}
 // prmt.b32 in its generic mode: selector nibble bit 3 replicates the sign bit of the selected byte
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;

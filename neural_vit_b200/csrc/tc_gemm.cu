@@ -217,7 +217,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       const uint32_t a_lbo = sh.a_lbo, b_lbo = sh.b_lbo, a_sbo = sh.a_sbo, b_sbo = sh.b_sbo;
-      const uint32_t a_kstep = sh.a_kstep, b_kstep = sh.b_kstep;  // bytes per UMMA_K = 16
+      const uint32_t a_kq = sh.a_kstep >> 4, b_kq = sh.b_kstep >> 4;  // descriptor units (16 B) per UMMA_K = 16
+      const uint32_t a_hi = umma_desc_hi(a_sbo), b_hi = umma_desc_hi(b_sbo);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -236,13 +237,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint32_t sb = B_RES ? smem_u32(s_bres + kb * Cfg::kBBytes) : sa + Cfg::kABytes;
+          // descriptor low words once per k-block, stepped by (k-step >> 4); high words loop-invariant
+          const uint32_t da_lo = umma_desc_lo(sa, a_lbo), db_lo = umma_desc_lo(sb, b_lbo);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t da = umma_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
-              const uint64_t db = umma_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
-              umma_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_ss(tmem_d, umma_desc(da_lo + k * a_kq, a_hi), umma_desc(db_lo + k * b_kq, b_hi), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
             tc_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
           }
           __syncwarp();
@@ -267,6 +268,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (tile / sh.n_tiles) * kBM, n0 = (tile % sh.n_tiles) * BN;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      // Epilogue operands that come from HBM (fp32 residual rows, bf16 pre-activations): request the NEXT tile's
+      // row segment of this thread into L2 now, one epilogue period ahead of the loads that consume it.
+      if ((EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_GELU_BWD) && ep.vec16_ok && w + w_step < total_work) {
+        const int tn = (w + w_step) / sh.splits;
+        const int mn = (tn / sh.n_tiles) * kBM + q * 32 + lane, nn = (tn % sh.n_tiles) * BN + half * (BN / kGroups);
+        if (mn < sh.M && nn < sh.N) {
+          if (EPI == TVIT_EPI_RESIDUAL) {
+            const float* r = ep.resid + (long long)mn * ep.ldres + nn;
+#pragma unroll
+            for (int j = 0; j < (BN / kGroups) * 4 / 128; ++j) l2_prefetch_line(r + 32 * j);
+          } else {
+            l2_prefetch_line((const __nv_bfloat16*)ep.aux + (long long)mn * ep.ldaux + nn);
+          }
+        }
+      }
       // stage this tile's per-column vectors (bias, LayerScale gamma) in shared memory: one element per epilogue
       // thread, double-buffered by accumulator stage; the named barrier also orders the buffer's previous readers
       float* sb = s_cols + as * 512;
