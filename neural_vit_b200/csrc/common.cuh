@@ -111,30 +111,29 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
-// Fast GELU pair for the bf16 tensor-core epilogues: erfc by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7,
-// two MUFU ops) -- far inside bf16 resolution; the fp32 verification path keeps erff above.
-//   phi_cdf(x) = 0.5 erfc(-x / sqrt 2);   gelu = x * cdf;   gelu' = cdf + x * pdf
-__device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& pdf) {
-  // t = 1 / (1 + p |x| / sqrt2);  e = exp(-x^2/2);  0.5 erfc(|x|/sqrt2) = t (a1/2 + t (a2/2 + ...)) e
-  const float t = rcp_approx(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.0f));
-  const float e = ex2_approx(x * x * (-0.5f * 1.4426950408889634f));
-  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
-  poly = fmaf(poly, t, 0.5f * 1.421413741f);
-  poly = fmaf(poly, t, 0.5f * -0.284496736f);
-  poly = fmaf(poly, t, 0.5f * 0.254829592f);
-  const float half_erfc = poly * t * e;
-  cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
-  pdf = 0.39894228040143268f * e;
+// Fast GELU pair for the bf16 tensor-core epilogues.  The normal CDF is evaluated without any MUFU operation as
+//   Phi(x) = sat(0.5 + x P(min(x^2, 16))),  P = degree-7 minimax fit of (Phi(x) - 0.5) / x on |x| <= 4
+// (|Phi error| <= 5.4e-5, relative Frobenius error of gelu over [-6, 6] 6e-5: far inside bf16 resolution; beyond
+// |x| = 4 the saturating FMA clamps to 0 / 1).  The GELU epilogues are bound by issue slots and the 16-lane MUFU
+// pipe, which the earlier erfc form (rcp + ex2 per element) loaded twice per element.  The fp32 verification path
+// keeps erff above.
+__device__ __forceinline__ float phi_cdf_fast(float x, float t) {
+  const float tc = fminf(t, 16.0f);
+  float p = fmaf(-1.5809006326250596e-09f, tc, 1.2171747698630497e-07f);
+  p = fmaf(p, tc, -4.10100710723782e-06f);
+  p = fmaf(p, tc, 8.066896407399327e-05f);
+  p = fmaf(p, tc, -0.00104821368586272f);
+  p = fmaf(p, tc, 0.009664901532232761f);
+  p = fmaf(p, tc, -0.0661754161119461f);
+  p = fmaf(p, tc, 0.3988475203514099f);
+  return __saturatef(fmaf(x, p, 0.5f));
 }
-__device__ __forceinline__ float gelu_fast(float x) {
-  float c, p;
-  gelu_fast_parts(x, c, p);
-  return x * c;
-}
+__device__ __forceinline__ float gelu_fast(float x) { return x * phi_cdf_fast(x, x * x); }
+// gelu'(x) = Phi(x) + x pdf(x),  pdf = exp(-x^2 / 2) / sqrt(2 pi): one ex2
 __device__ __forceinline__ float gelu_grad_fast(float x) {
-  float c, p;
-  gelu_fast_parts(x, c, p);
-  return fmaf(x, p, c);
+  const float t = x * x;
+  const float e = ex2_approx(t * (-0.5f * 1.4426950408889634f));
+  return fmaf(x * e, 0.39894228040143268f, phi_cdf_fast(x, t));
 }
 template <typename T> __device__ __forceinline__ float gelu_t(float x) { return sizeof(T) == 2 ? gelu_fast(x) : gelu_f(x); }
 template <typename T> __device__ __forceinline__ float gelu_grad_t(float x) {
@@ -142,9 +141,13 @@ template <typename T> __device__ __forceinline__ float gelu_grad_t(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// counter-based dropout RNG: Philox4x32-7, 16 random bits per element, 8 elements per call.
-// keep(e) <=> bits16(e) >= thr16, thr16 = round(p * 65536).  A mask is a pure function of
-// (seed, site, element index), so forward and backward regenerate it without storing it.
+// Counter-based dropout RNG.  A mask is a pure function of (seed, site, element index), so forward and backward
+// regenerate it without storing it.  One Philox4x32-7 call serves 16 consecutive elements with 8 random bits
+// each.  An 8-bit compare alone would quantise p to 1/256, so the threshold of each 16-element group is dithered:
+//   T_g = (thr16 >> 8) + [weyl8(g, seed) < (thr16 & 255)],   keep(e) <=> byte(e) >= T_g,   thr16 = round(65536 p),
+// where weyl8 is the top byte of a golden-ratio Weyl sequence over the group index.  With the dither counted as
+// part of the generator every element is dropped with probability exactly thr16 / 65536; the elements of one
+// group share T_g, a correlation of about 4e-5.
 // ---------------------------------------------------------------------------------------------
 struct DropCfg {
   unsigned long long seed;
@@ -209,60 +212,59 @@ __device__ __forceinline__ uint4 philox4x32_7(const DropCfg& c, unsigned long lo
   return make_uint4(c0, c1, c2, c3);
 }
 
-// random 16-bit lanes for the 8 consecutive elements [8*g, 8*g+8)
-__device__ __forceinline__ void drop_bits8(const DropCfg& c, unsigned long long group, uint32_t out[4]) {
-  uint4 r = philox4x32_7(c, group);
-  out[0] = r.x;
-  out[1] = r.y;
-  out[2] = r.z;
-  out[3] = r.w;
-}
-// multiplier (0 or 1/(1-p)) for a single element index
-__device__ __forceinline__ float drop_mult(const DropCfg& c, unsigned long long e) {
-  if (c.thr16 == 0) return 1.0f;
-  uint32_t w[4];
-  drop_bits8(c, e >> 3, w);
-  const unsigned int j = (unsigned int)(e & 7ull);
-  const unsigned int k = j >> 1;  // selects instead of a dynamic index: keeps w[] out of local memory
-  const uint32_t ww = k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3]));
-  const uint32_t bits = (ww >> ((j & 1u) * 16u)) & 0xffffu;
-  return bits >= c.thr16 ? c.inv_keep : 0.0f;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Attention-probability dropout (the N x N site): 16 elements per Philox call, 8 random bits per element.
-// An 8-bit compare alone would quantise p to 1/256, so the threshold of each 16-element group is dithered:
-//   T_g = (thr16 >> 8) + [weyl8(g, seed) < (thr16 & 255)],   keep(e) <=> byte(e) >= T_g,
-// where weyl8 is the top byte of a golden-ratio Weyl sequence over the group index.  With the dither counted as
-// part of the generator, every element is dropped with probability exactly thr16 / 65536 (the same marginal as the
-// 16-bit scheme used by the GEMM epilogues); elements of one group share T_g, a correlation of ~4e-5.
-// Element index: row-major over (b, h, q, k) with the k extent padded to a multiple of 16 so that groups never
-// straddle rows; forward, backward and the SIMT verification path all use these helpers.
-// ---------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ unsigned long long attn_drop_row_base(int b, int H, int h, int N, int q) {
-  const unsigned long long npad = (unsigned long long)((N + 15) & ~15);
-  return (((unsigned long long)b * H + h) * N + q) * npad;
-}
-__device__ __forceinline__ uint32_t attn_drop_thr8(const DropCfg& c, unsigned long long group16) {
-  const uint32_t weyl = ((uint32_t)group16 * 0x9E3779B1u + (uint32_t)c.seed) >> 24;
+// group threshold T_g in [0, 256]
+__device__ __forceinline__ uint32_t drop_thr8(const DropCfg& c, unsigned long long group16) {
+  const uint32_t weyl = ((uint32_t)group16 * 0x9E3779B1u + c.rk0[0]) >> 24;
   return (c.thr16 >> 8) + (weyl < (c.thr16 & 255u) ? 1u : 0u);
 }
 // random bytes for the 16 consecutive elements [16 g, 16 g + 16): element j is byte (j & 3) of word j >> 2
-__device__ __forceinline__ void attn_drop_bits16(const DropCfg& c, unsigned long long group16, uint32_t out[4]) {
+__device__ __forceinline__ void drop_bits16(const DropCfg& c, unsigned long long group16, uint32_t out[4]) {
   uint4 r = philox4x32_7(c, group16);
   out[0] = r.x;
   out[1] = r.y;
   out[2] = r.z;
   out[3] = r.w;
 }
-// keep flag of a single element (SIMT verification path)
-__device__ __forceinline__ bool attn_drop_keep(const DropCfg& c, unsigned long long e) {
+// keep flag / multiplier (0 or 1/(1-p)) of a single element
+__device__ __forceinline__ bool drop_keep(const DropCfg& c, unsigned long long e) {
   if (c.thr16 == 0) return true;
   uint32_t w[4];
-  attn_drop_bits16(c, e >> 4, w);
+  drop_bits16(c, e >> 4, w);
   const unsigned int j = (unsigned int)(e & 15ull), k = j >> 2;
+  const uint32_t ww = k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3]));  // selects keep w[] in registers
+  return ((ww >> ((j & 3u) * 8u)) & 0xffu) >= drop_thr8(c, e >> 4);
+}
+__device__ __forceinline__ float drop_mult(const DropCfg& c, unsigned long long e) {
+  return drop_keep(c, e) ? c.inv_keep : 0.0f;
+}
+// multipliers of the four elements e..e+3, e % 4 == 0 (one word of the group)
+__device__ __forceinline__ void drop_mult4(const DropCfg& c, unsigned long long e, float m[4]) {
+  if (c.thr16 == 0) {
+    m[0] = m[1] = m[2] = m[3] = 1.0f;
+    return;
+  }
+  uint32_t w[4];
+  drop_bits16(c, e >> 4, w);
+  const uint32_t t = drop_thr8(c, e >> 4);
+  const unsigned int k = (unsigned int)(e >> 2) & 3u;
   const uint32_t ww = k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3]));
-  return ((ww >> ((j & 3u) * 8u)) & 0xffu) >= attn_drop_thr8(c, e >> 4);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m[j] = (((ww >> (8 * j)) & 0xffu) >= t) ? c.inv_keep : 0.f;
+}
+// multipliers of the 16 elements e..e+15, e % 16 == 0: one Philox call
+__device__ __forceinline__ void drop_mult16(const DropCfg& c, unsigned long long e, float m[16]) {
+  uint32_t w[4];
+  drop_bits16(c, e >> 4, w);
+  const uint32_t t = drop_thr8(c, e >> 4);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) m[j] = (((w[j >> 2] >> (8 * (j & 3))) & 0xffu) >= t) ? c.inv_keep : 0.f;
+}
+
+// Attention-probability dropout (the N x N site) element index: row-major over (b, h, q, k) with the k extent
+// padded to a multiple of 16 so that groups never straddle rows (forward, backward and the SIMT path agree).
+__host__ __device__ __forceinline__ unsigned long long attn_drop_row_base(int b, int H, int h, int N, int q) {
+  const unsigned long long npad = (unsigned long long)((N + 15) & ~15);
+  return (((unsigned long long)b * H + h) * N + q) * npad;
 }
 
 }  // namespace tvit

@@ -15,22 +15,6 @@ static inline int blocks_for(long long work, int per_block, int max_blocks) {
   return (int)b;
 }
 
-// four dropout multipliers for elements e..e+3 (e % 4 == 0)
-__device__ __forceinline__ void drop_mult4(const DropCfg& c, unsigned long long e, float m[4]) {
-  if (c.thr16 == 0) {
-    m[0] = m[1] = m[2] = m[3] = 1.0f;
-    return;
-  }
-  uint32_t w[4];
-  drop_bits8(c, e >> 3, w);
-  const bool hi = ((e >> 2) & 1ull) != 0ull;  // selects, not a dynamic index (keeps w[] in registers)
-  const uint32_t w0 = hi ? w[2] : w[0], w1 = hi ? w[3] : w[1];
-  m[0] = ((w0 & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
-  m[1] = ((w0 >> 16) >= c.thr16) ? c.inv_keep : 0.f;
-  m[2] = ((w1 & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
-  m[3] = ((w1 >> 16) >= c.thr16) ? c.inv_keep : 0.f;
-}
-
 // ---------------------------------------------------------------------------------------------
 // im2col: x (B,K,F,T) fp32 -> cols [B*n, P] act.  V = 4 elements per thread when pt % 4 == 0.
 // Threads are ordered by OUTPUT element so stores are fully coalesced; each load is a whole

@@ -57,27 +57,19 @@ inline EpiParams make_epi_params(const tvit_gemm_args* a) {
   return p;
 }
 
+// four multipliers for e..e+3 with arbitrary alignment
 __device__ __forceinline__ void drop_mult4e(const DropCfg& c, unsigned long long e, float m[4]) {
   if (c.thr16 == 0) {
     m[0] = m[1] = m[2] = m[3] = 1.0f;
-    return;
-  }
-  if ((e & 3ull) == 0ull) {
-    uint32_t w[4];
-    drop_bits8(c, e >> 3, w);
-    const bool hi = ((e >> 2) & 1ull) != 0ull;  // selects, not a dynamic index (keeps w[] in registers)
-    const uint32_t w0 = hi ? w[2] : w[0], w1 = hi ? w[3] : w[1];
-    m[0] = ((w0 & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
-    m[1] = ((w0 >> 16) >= c.thr16) ? c.inv_keep : 0.f;
-    m[2] = ((w1 & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
-    m[3] = ((w1 >> 16) >= c.thr16) ? c.inv_keep : 0.f;
+  } else if ((e & 3ull) == 0ull) {
+    drop_mult4(c, e, m);
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) m[j] = drop_mult(c, e + j);
   }
 }
 
-// 8 multipliers for e..e+7, e % 8 == 0: one Philox call
+// 8 multipliers for e..e+7, e % 8 == 0
 __device__ __forceinline__ void drop_mult8(const DropCfg& c, unsigned long long e, float m[8]) {
   if (c.thr16 == 0) {
 #pragma unroll
@@ -85,11 +77,14 @@ __device__ __forceinline__ void drop_mult8(const DropCfg& c, unsigned long long 
     return;
   }
   uint32_t w[4];
-  drop_bits8(c, e >> 3, w);
+  drop_bits16(c, e >> 4, w);
+  const uint32_t t = drop_thr8(c, e >> 4);
+  const bool hi = ((e >> 3) & 1ull) != 0ull;  // second half of the 16-element group
+  const uint32_t w0 = hi ? w[2] : w[0], w1 = hi ? w[3] : w[1];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    m[2 * j] = ((w[j] & 0xffffu) >= c.thr16) ? c.inv_keep : 0.f;
-    m[2 * j + 1] = ((w[j] >> 16) >= c.thr16) ? c.inv_keep : 0.f;
+    m[j] = (((w0 >> (8 * j)) & 0xffu) >= t) ? c.inv_keep : 0.f;
+    m[4 + j] = (((w1 >> (8 * j)) & 0xffu) >= t) ? c.inv_keep : 0.f;
   }
 }
 
@@ -322,8 +317,7 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
   }
   float ml[16];
   if (kDrop) {
-    drop_mult8(p.drop, (unsigned long long)m * p.N + nc, ml);
-    drop_mult8(p.drop, (unsigned long long)m * p.N + nc + 8, ml + 8);
+    drop_mult16(p.drop, (unsigned long long)m * p.N + nc, ml);  // vec16_ok: N % 16 == 0 and nc % 16 == 0
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) ml[j] = 1.0f;  // folded away by the compiler

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) simt_attn_fwd_kernel(const T* __restrict_
     const float corr = __expf(mx - mn);
     const float p = __expf(s - mn);
     l = l * corr + p;
-    const float pm = attn_drop_keep(drop, rowe + k) ? p * drop.inv_keep : 0.f;
+    const float pm = drop_keep(drop, rowe + k) ? p * drop.inv_keep : 0.f;
 #pragma unroll
     for (int j = 0; j < HPL; ++j) o[j] = o[j] * corr + pm * Act<T>::ld(vr + lane + 32 * j);
     mx = mn;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128) simt_attn_bwd_kernel(const T* __restrict_
     s = warp_sum(s) * scale;
     dpd = warp_sum(dpd);
     const float p = __expf(s - L);
-    const float mlt = attn_drop_keep(drop, rowe + k) ? drop.inv_keep : 0.f;
+    const float mlt = drop_keep(drop, rowe + k) ? drop.inv_keep : 0.f;
     const float ds = p * (dpd * mlt - dsum) * scale;
     const float pd = p * mlt;
 #pragma unroll

@@ -209,8 +209,8 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
         for (int g = 0; g < 2; ++g) {  // one Philox call per 16 keys (common.cuh: attention-probability dropout)
           uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0;
           if (kDrop) {
-            attn_drop_bits16(drop, g0 + c2 * 2 + g, w);
-            tg2 = attn_drop_thr8(drop, g0 + c2 * 2 + g) * 0x10001u;
+            drop_bits16(drop, g0 + c2 * 2 + g, w);
+            tg2 = drop_thr8(drop, g0 + c2 * 2 + g) * 0x10001u;
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {

@@ -294,8 +294,8 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0;
         if (kDrop) {  // this thread's 16 keys are exactly one Philox group (common.cuh)
           const unsigned long long grp = (rowe >> 4) + (unsigned long long)(hf * 4 + chunk);
-          attn_drop_bits16(drop, grp, w);
-          tg2 = attn_drop_thr8(drop, grp) * 0x10001u;
+          drop_bits16(drop, grp, w);
+          tg2 = drop_thr8(drop, grp) * 0x10001u;
         }
 #pragma unroll
         for (int t = 0; t < 8; ++t) {  // element pairs (2t, 2t+1)

@@ -86,7 +86,7 @@ struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
-                                    4096 /*bias + gamma staging, 2 tiles x 2 x 256 fp32*/;
+                                    8192 /*bias + gamma staging, 1 KB per epilogue warp*/;
 };
 
 struct GemmShape {
@@ -120,7 +120,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = bars + 2 * kStages + 2;
   uint64_t* bres_bar = bars + 2 * kStages + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
-  float* s_cols = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 stages][bias 256 | gamma 256]
+  float* s_cols = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [epilogue warp][bias W | gamma W]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -283,17 +283,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      // stage this tile's per-column vectors (bias, LayerScale gamma) in shared memory: one element per epilogue
-      // thread, double-buffered by accumulator stage; the named barrier also orders the buffer's previous readers
-      float* sb = s_cols + as * 512;
+      // Stage the per-column vectors (bias, LayerScale gamma) of this warp's column group in a warp-private slice of
+      // shared memory: only __syncwarp is needed, so the epilogue warps never wait for each other.
+      constexpr int kW = BN / kGroups;  // columns per warp
+      float* sb = s_cols + (warp - 4) * (2 * kW);
       {
-        const int e = (int)threadIdx.x - 128;
-        const int col = n0 + e;
-        if (e < BN) {
+        __syncwarp();  // the previous tile's reads of this slice are done
+#pragma unroll
+        for (int j = 0; j < kW / 32; ++j) {
+          const int e = j * 32 + lane, col = n0 + half * kW + e;
           sb[e] = (ep.bias && col < sh.N) ? ep.bias[col] : 0.f;
-          sb[256 + e] = (ep.gamma && col < sh.N) ? ep.gamma[col] : 1.f;
+          sb[kW + e] = (ep.gamma && col < sh.N) ? ep.gamma[col] : 1.f;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(EpiCfg<BN>::kEpiThreads) : "memory");
+        __syncwarp();
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -312,8 +314,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (nc >= sh.N) break;  // warp-uniform (N % 16 == 0 on this path is implied by vec8_ok only for N % 8;
                                   // a trailing 8-column piece falls to the generic path below)
           if (nc + 16 <= sh.N) {
-            tc_epi16<EPI, kDrop>(ep, sb_addr + (uint32_t)(u * 64), sb_addr + 1024u + (uint32_t)(u * 64), rsc, m, nc,
-                          taddr + (uint32_t)(u * 16), row_ok);
+            const uint32_t so = sb_addr + (uint32_t)((u - half * kHalfSub) * 64);
+            tc_epi16<EPI, kDrop>(ep, so, so + (uint32_t)(kW * 4), rsc, m, nc, taddr + (uint32_t)(u * 16), row_ok);
           } else {
             uint32_t r[16];
             tmem_ld16(taddr + (uint32_t)(u * 16), r);
@@ -365,7 +367,7 @@ template <int BN, bool MN, int EPI, bool kDrop, bool B_RES = false>
 static int launch_tc_d(const tvit_gemm_args* a, const GemmShape& sh, const EpiParams& ep, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
   auto kern = tc_gemm_kernel<BN, MN, MN, EPI, kDrop, B_RES>;
-  constexpr int kSmem = B_RES ? (kMaxResKBlocks * Cfg::kBBytes + 4 * Cfg::kABytes + 1024 + 256 + 4096) : Cfg::kSmemBytes;
+  constexpr int kSmem = B_RES ? (kMaxResKBlocks * Cfg::kBBytes + 4 * Cfg::kABytes + 1024 + 256 + 8192) : Cfg::kSmemBytes;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
