@@ -268,9 +268,24 @@ __device__ __forceinline__ void st_bf16x16(__nv_bfloat16* o, const float (&x)[16
   st_global_v8(o, v);
 }
 
+// Per-thread epilogue operands that come from global memory for one 16-column chunk: the fp32 residual row
+// (RESIDUAL, 16 words) or the bf16 pre-activations (GELU_BWD, 8 words).  Split from tc_epi16 so that the caller can
+// request chunk u+1 before it processes chunk u (two chunks of loads in flight per thread).
+template <int EPI>
+__device__ __forceinline__ void tc_epi16_load(const EpiParams& p, int m, int nc, bool row_ok, uint32_t (&ext)[16]) {
+  if (EPI == TVIT_EPI_RESIDUAL && row_ok) {
+    const float* r = p.resid + m * p.ldres + nc;
+    ld_global_v8(r, *reinterpret_cast<uint32_t(*)[8]>(&ext[0]));
+    ld_global_v8(r + 8, *reinterpret_cast<uint32_t(*)[8]>(&ext[8]));
+  }
+  if (EPI == TVIT_EPI_GELU_BWD && row_ok) {
+    ld_global_v8((const __nv_bfloat16*)p.aux + m * p.ldaux + nc, *reinterpret_cast<uint32_t(*)[8]>(&ext[0]));
+  }
+}
+
 template <int EPI, bool kDrop>
 __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, uint32_t s_gamma, float row_scale, int m,
-                                         int nc, uint32_t taddr, bool row_ok) {
+                                         int nc, uint32_t taddr, bool row_ok, const uint32_t (&ext)[16]) {
   constexpr bool kBias = (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL);
   uint32_t acc[16];
   asm volatile(
@@ -282,7 +297,6 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
       : "r"(taddr)
       : "memory");
   float4 b[4], g[4];
-  uint32_t res[16], hx[8];
   if (kBias) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) b[j] = ld_shared_f4(s_bias + 16 * j);
@@ -290,14 +304,6 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
   if (EPI == TVIT_EPI_RESIDUAL) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) g[j] = ld_shared_f4(s_gamma + 16 * j);
-    if (row_ok) {
-      const float* r = p.resid + m * p.ldres + nc;
-      ld_global_v8(r, *reinterpret_cast<uint32_t(*)[8]>(&res[0]));
-      ld_global_v8(r + 8, *reinterpret_cast<uint32_t(*)[8]>(&res[8]));
-    }
-  }
-  if (EPI == TVIT_EPI_GELU_BWD && row_ok) {
-    ld_global_v8((const __nv_bfloat16*)p.aux + m * p.ldaux + nc, hx);
   }
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   if (!row_ok) return;
@@ -334,13 +340,13 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
     uint32_t ov[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      ov[j] = __float_as_uint(fmaf(row_scale * gg[j], x[j] * ml[j], __uint_as_float(res[j])));
+      ov[j] = __float_as_uint(fmaf(row_scale * gg[j], x[j] * ml[j], __uint_as_float(ext[j])));
     st_global_v8(o, *reinterpret_cast<uint32_t(*)[8]>(&ov[0]));
     st_global_v8(o + 8, *reinterpret_cast<uint32_t(*)[8]>(&ov[8]));
   } else if (EPI == TVIT_EPI_GELU_BWD) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hx[t]));
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ext[t]));
       x[2 * t] *= ml[2 * t] * gelu_grad_fast(f.x);
       x[2 * t + 1] *= ml[2 * t + 1] * gelu_grad_fast(f.y);
     }

@@ -297,25 +297,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < sh.M;
+      // global epilogue operands are double-buffered in registers: chunk u+1 is requested before chunk u is
+      // processed (and the first chunk before the accumulator is even complete), so every thread keeps two chunks
+      // of loads in flight; they hit L2 thanks to the prefetch above
+      uint32_t ext[2][16];
+      constexpr bool kExt = (EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_GELU_BWD);
+      constexpr int kHalfSub = BN / 16 / kGroups;
+      if (kExt && ep.vec16_ok && n0 + half * kHalfSub * 16 + 16 <= sh.N)
+        tc_epi16_load<EPI>(ep, m, n0 + half * kHalfSub * 16, row_ok, ext[0]);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       constexpr bool kFast = (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL ||
                               EPI == TVIT_EPI_GELU_BWD);
       if (kFast && ep.vec16_ok) {
         const float rsc = (EPI == TVIT_EPI_RESIDUAL && ep.row_scale && row_ok) ? ep.row_scale[m / ep.rpg] : 1.0f;
         const uint32_t sb_addr = smem_u32(sb);
-        constexpr int kSub = BN / 16, kHalfSub = kSub / kGroups;
-#pragma unroll 1
-        for (int u = half * kHalfSub; u < (half + 1) * kHalfSub; ++u) {
+#pragma unroll
+        for (int uu = 0; uu < kHalfSub; ++uu) {
+          const int u = half * kHalfSub + uu;
           const int nc = n0 + u * 16;
           if (nc >= sh.N) break;  // warp-uniform (N % 16 == 0 on this path is implied by vec8_ok only for N % 8;
                                   // a trailing 8-column piece falls to the generic path below)
           if (nc + 16 <= sh.N) {
-            const uint32_t so = sb_addr + (uint32_t)((u - half * kHalfSub) * 64);
-            tc_epi16<EPI, kDrop>(ep, so, so + (uint32_t)(kW * 4), rsc, m, nc, taddr + (uint32_t)(u * 16), row_ok);
+            if (kExt && uu + 1 < kHalfSub && nc + 32 <= sh.N) tc_epi16_load<EPI>(ep, m, nc + 16, row_ok, ext[(uu + 1) & 1]);
+            const uint32_t so = sb_addr + (uint32_t)(uu * 64);
+            tc_epi16<EPI, kDrop>(ep, so, so + (uint32_t)(kW * 4), rsc, m, nc, taddr + (uint32_t)(u * 16), row_ok,
+                                 ext[uu & 1]);
           } else {
             uint32_t r[16];
             tmem_ld16(taddr + (uint32_t)(u * 16), r);
