@@ -38,6 +38,9 @@ enum { TVIT_ENGINE_SIMT = 0, TVIT_ENGINE_TCGEN05 = 1 };
 
 /* Counter-based dropout descriptor: mask(e) is a pure function of (seed, site, element index e),
  * so backward regenerates the mask forward used.  p == 0 disables dropout.
+ * One Philox4x32-7 call covers the 16 elements [16 g, 16 g + 16) with 8 random bits each; the 8-bit threshold of
+ * each group is dithered (golden-ratio Weyl sequence over g) so that every element is dropped with probability
+ * round(65536 p) / 65536 exactly; kept elements are scaled by 1 / (1 - that probability).
  * Replaces nn.Dropout's ATen Philox stream (model.py:102,104,138,140,224,250). */
 typedef struct {
   unsigned long long seed;
@@ -112,7 +115,7 @@ int tvit_gemm(const tvit_gemm_args* args, tvit_stream_t stream);
  * no B*H*N*N tensor is materialised; only the per-row log-sum-exp is kept for backward.
  *   qkv : [B*N, 3*H*hd] act, columns ordered [q(all heads) | k | v], head h = cols h*hd..(h+1)*hd
  *   out : [B*N, H*hd] act (token-major, heads merged)       lse : [B, H, N] fp32 (natural log)
- * Dropout on the probabilities: element index = ((b*H + h)*N + q)*Np + k, Np = N rounded up to 8.
+ * Dropout on the probabilities: element index = ((b*H + h)*N + q)*Np + k, Np = N rounded up to 16.
  * Replaces model.py:108-115 (reshape/permute, q@k^T*scale, softmax, attn_drop, @v, transpose).
  * ------------------------------------------------------------------------------------------- */
 int tvit_attn_fwd(int engine, int dtype, const void* qkv, void* out, float* lse, int B, int N, int H, int hd,
