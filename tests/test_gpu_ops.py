@@ -316,6 +316,32 @@ def test_elementwise_dropout_statistics_and_replay(dtype):
     assert torch.equal(out != 0, keep)
 
 
+@pytest.mark.parametrize("p", [0.1, 0.123, 0.5, 1.0 / 256.0, 0.9])
+def test_dropout_rate_is_exact_despite_8bit_lanes(p):
+    """16 elements share one Philox call (8 random bits each); the per-group threshold dither must make the drop
+    probability equal p to ~2^-16, not p rounded to 1/256: over 2^24 elements the binomial std of the keep rate is
+    below 1.3e-4, while p = 0.123 rounded to 31/256 or 32/256 would be off by 1.9e-3 / 2e-3."""
+    rows, D = 1 << 14, 1 << 10
+    g = torch.ones((rows, D), device=DEV)
+    gp = torch.empty((rows, D), dtype=torch.float32, device=DEV)
+    cs = torch.zeros(D, device=DEV)
+    ops.branch_grad_prep(g, rows, D, None, 1, (20240607, 3, p), gp, L.F32, cs)
+    keep = gp != 0
+    rate = keep.double().mean().item()
+    assert abs(rate - (1 - p)) < 6e-4, rate
+    vals = gp[keep]
+    assert torch.allclose(vals, torch.full_like(vals, 1 / (1 - p)), rtol=1e-4)
+    # no structure along rows or columns: per-column and per-row keep rates are binomial around 1 - p
+    col, row = keep.double().mean(0), keep.double().mean(1)
+    sd_c, sd_r = math.sqrt(p * (1 - p) / rows), math.sqrt(p * (1 - p) / D)
+    assert (col - (1 - p)).abs().max().item() < 6 * sd_c + 1e-4
+    assert (row - (1 - p)).abs().max().item() < 6 * sd_r + 1e-4
+    # neighbouring elements inside a 16-element group are (almost) uncorrelated
+    k = keep.double()
+    c = ((k[:, :-1] - (1 - p)) * (k[:, 1:] - (1 - p))).mean().item() / (p * (1 - p))
+    assert abs(c) < 2e-3, c
+
+
 def test_embed_backward_pieces():
     Bsz, Kp, Fp, Tp, D = 3, 2, 3, 4, 64
     n = Kp * Fp * Tp
