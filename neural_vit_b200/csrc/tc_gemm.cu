@@ -268,20 +268,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (tile / sh.n_tiles) * kBM, n0 = (tile % sh.n_tiles) * BN;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      // Epilogue operands that come from HBM (fp32 residual rows, bf16 pre-activations): request the NEXT tile's
-      // row segment of this thread into L2 now, one epilogue period ahead of the loads that consume it.
-      if ((EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_GELU_BWD) && ep.vec16_ok && w + w_step < total_work) {
+      // GELU_BWD: request the NEXT tile's bf16 pre-activations (this thread's row segment) into L2 now, one epilogue
+      // period ahead of the loads that consume them (-0.8 ms per step).  Not done for the fp32 residual rows of
+      // RESIDUAL: with the register double-buffering below it bought nothing there and ncu showed the rows being
+      // fetched from DRAM twice (+30 % read traffic).
+      if (EPI == TVIT_EPI_GELU_BWD && ep.vec16_ok && w + w_step < total_work) {
         const int tn = (w + w_step) / sh.splits;
         const int mn = (tn / sh.n_tiles) * kBM + q * 32 + lane, nn = (tn % sh.n_tiles) * BN + half * (BN / kGroups);
-        if (mn < sh.M && nn < sh.N) {
-          if (EPI == TVIT_EPI_RESIDUAL) {
-            const float* r = ep.resid + (long long)mn * ep.ldres + nn;
-#pragma unroll
-            for (int j = 0; j < (BN / kGroups) * 4 / 128; ++j) l2_prefetch_line(r + 32 * j);
-          } else {
-            l2_prefetch_line((const __nv_bfloat16*)ep.aux + (long long)mn * ep.ldaux + nn);
-          }
-        }
+        if (mn < sh.M && nn < sh.N) l2_prefetch_line((const __nv_bfloat16*)ep.aux + (long long)mn * ep.ldaux + nn);
       }
       // Stage the per-column vectors (bias, LayerScale gamma) of this warp's column group in a warp-private slice of
       // shared memory: only __syncwarp is needed, so the epilogue warps never wait for each other.
@@ -301,7 +295,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = m < sh.M;
       // global epilogue operands are double-buffered in registers: chunk u+1 is requested before chunk u is
       // processed (and the first chunk before the accumulator is even complete), so every thread keeps two chunks
-      // of loads in flight; they hit L2 thanks to the prefetch above
+      // of loads in flight
       uint32_t ext[2][16];
       constexpr bool kExt = (EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_GELU_BWD);
       constexpr int kHalfSub = BN / 16 / kGroups;
