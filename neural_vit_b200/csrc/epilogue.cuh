@@ -321,6 +321,32 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
     st_bf16x16((__nv_bfloat16*)p.out + m * p.ldo + nc, x);
     return;
   }
+  // bf16 outputs: the dropout keep masks are applied to packed bf16 pairs (one Philox call, then two prmt and an
+  // integer subtract per pair), the 1/(1-p) factor is one multiply; fp32 outputs use per-element multipliers.
+  const float keep_scale = kDrop ? p.drop.inv_keep : 1.0f;
+  if (EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_GELU_BWD) {
+    uint32_t mk[8];
+    if (kDrop) drop_keep_masks16(p.drop, (unsigned long long)m * p.N + nc, mk);  // vec16_ok: N, nc % 16 == 0
+    uint32_t v[8];
+    if (EPI == TVIT_EPI_BIAS_GELU) {
+      st_bf16x16((__nv_bfloat16*)p.aux + m * p.ldaux + nc, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = pack_bf16(gelu_fast(x[2 * j]) * keep_scale, gelu_fast(x[2 * j + 1]) * keep_scale);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ext[j]));
+        v[j] = pack_bf16(x[2 * j] * keep_scale * gelu_grad_fast(f.x), x[2 * j + 1] * keep_scale * gelu_grad_fast(f.y));
+      }
+    }
+    if (kDrop) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] &= mk[j];
+    }
+    st_global_v8((__nv_bfloat16*)p.out + m * p.ldo + nc, v);
+    return;
+  }
   float ml[16];
   if (kDrop) {
     drop_mult16(p.drop, (unsigned long long)m * p.N + nc, ml);  // vec16_ok: N % 16 == 0 and nc % 16 == 0
@@ -328,12 +354,7 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
 #pragma unroll
     for (int j = 0; j < 16; ++j) ml[j] = 1.0f;  // folded away by the compiler
   }
-  if (EPI == TVIT_EPI_BIAS_GELU) {
-    st_bf16x16((__nv_bfloat16*)p.aux + m * p.ldaux + nc, x);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) x[j] = gelu_fast(x[j]) * ml[j];
-    st_bf16x16((__nv_bfloat16*)p.out + m * p.ldo + nc, x);
-  } else if (EPI == TVIT_EPI_RESIDUAL) {
+  if (EPI == TVIT_EPI_RESIDUAL) {
     float* o = (float*)p.out + m * p.ldo + nc;
     const float gg[16] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w,
                           g[2].x, g[2].y, g[2].z, g[2].w, g[3].x, g[3].y, g[3].z, g[3].w};
@@ -343,14 +364,6 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
       ov[j] = __float_as_uint(fmaf(row_scale * gg[j], x[j] * ml[j], __uint_as_float(ext[j])));
     st_global_v8(o, *reinterpret_cast<uint32_t(*)[8]>(&ov[0]));
     st_global_v8(o + 8, *reinterpret_cast<uint32_t(*)[8]>(&ov[8]));
-  } else if (EPI == TVIT_EPI_GELU_BWD) {
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ext[t]));
-      x[2 * t] *= ml[2 * t] * gelu_grad_fast(f.x);
-      x[2 * t + 1] *= ml[2 * t + 1] * gelu_grad_fast(f.y);
-    }
-    st_bf16x16((__nv_bfloat16*)p.out + m * p.ldo + nc, x);
   }
 }
 

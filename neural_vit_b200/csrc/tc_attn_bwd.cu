@@ -304,7 +304,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           const float a0 = fmaf(__uint_as_float(dp[2 * t]), scale, negDq);
           const float a1 = fmaf(__uint_as_float(dp[2 * t + 1]), scale, negDq);
           if (kDrop) {
-            const uint32_t m = attn_keep_mask2(w[t >> 1], t & 1, tg2);
+            const uint32_t m = drop_keep_mask2(w[t >> 1], t & 1, tg2);
             const uint32_t kept = pack_bf16(p0 * a0, p1 * a1), dropped = pack_bf16(p0 * negDq, p1 * negDq);
             pk[t] = pack_bf16(p0, p1) & m;
             dk[t] = (kept & m) | (dropped & ~m);

@@ -289,19 +289,6 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
 __device__ __forceinline__ void l2_prefetch_line(const void* gptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr));
 }
-// prmt.b32 in its generic mode: selector nibble bit 3 replicates the sign bit of the selected byte
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-  return d;
-}
-// Keep mask (0xffff per kept bf16 lane) for two attention-dropout elements whose random bytes are bytes
-// (2 hi, 2 hi + 1) of w: lanes 0x8000 | byte, minus the group threshold in both lanes (tg2 = T_g * 0x10001,
-// T_g <= 256 so no borrow crosses lanes); bit 15 of a lane survives iff byte >= T_g and is then smeared.
-__device__ __forceinline__ uint32_t attn_keep_mask2(uint32_t w, int hi, uint32_t tg2) {
-  const uint32_t x = prmt(w, 0x80u, hi ? 0x4342u : 0x4140u);
-  return prmt(x - tg2, 0u, 0xBB99u);
-}
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
   return ((smem_addr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
 }
