@@ -107,18 +107,15 @@ static __device__ __noinline__ void mbar_timeout_trap(uint32_t parity) {
          (int)blockIdx.z, (int)threadIdx.x, parity);
   __trap();
 }
-// NOTE: %globaltimer is only sampled every 4096 failed polls -- reading it on every wait costs hundreds of
-// cycles and was the dominant cost of short pipeline hand-offs.
+// Hot-path wait: six instructions per failed poll.  A failed try_wait already blocks in hardware for ~20-100 clk, so
+// the poll count itself is the clock: 2^26 polls are > 1 s, three orders of magnitude above the longest legitimate
+// wait (an epilogue warp waiting out a whole split-K mainloop, ~0.5 ms).  The earlier version kept a spin counter
+// plus a sampled %globaltimer in every wait; ncu showed ~25 executed instructions per wait, i.e. ~15 % of the
+// instruction stream of the attention-backward softmax warps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
-  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xfffu) == 0u) {
-      const unsigned long long now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > TVIT_MBAR_TIMEOUT_NS) mbar_timeout_trap(parity);
-    }
+    if (++spins == (1u << 26)) mbar_timeout_trap(parity);
   }
 }
 
