@@ -260,26 +260,34 @@ __device__ __forceinline__ void drop_mult16(const DropCfg& c, unsigned long long
   for (int j = 0; j < 16; ++j) m[j] = (((w[j >> 2] >> (8 * (j & 3))) & 0xffu) >= t) ? c.inv_keep : 0.f;
 }
 
-// prmt.b32 in its generic mode: selector nibble bit 3 replicates the sign bit of the selected byte
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+// prmt.b32 in its generic mode: selector nibble bit 3 replicates the sign bit of the selected byte.  The selector is
+// a template argument so that it is encoded as an immediate (as a register operand ptxas re-materialised the
+// constant with a UMOV + move in front of every use).
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
   uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(SEL));
   return d;
 }
-// Keep mask (0xffff per kept bf16 lane) for two dropout elements whose random bytes are bytes
-// (2 hi, 2 hi + 1) of w: lanes 0x8000 | byte, minus the group threshold in both lanes (tg2 = T_g * 0x10001,
-// T_g <= 256 so no borrow crosses lanes); bit 15 of a lane survives iff byte >= T_g and is then smeared.
-__device__ __forceinline__ uint32_t drop_keep_mask2(uint32_t w, int hi, uint32_t tg2) {
-  const uint32_t x = prmt(w, 0x80u, hi ? 0x4342u : 0x4140u);
-  return prmt(x - tg2, 0u, 0xBB99u);
+// Keep mask (0xffff per kept bf16 lane) for two dropout elements whose random bytes are bytes (2 HI, 2 HI + 1) of
+// w: the bytes are spread into two 16-bit lanes, tgc = 0x80008000 - T_g * 0x10001 is added to both lanes (T_g <= 256,
+// so no carry crosses lanes) and bit 15 of a lane ends up set iff byte >= T_g; prmt then smears it over the lane.
+__device__ __forceinline__ uint32_t drop_tgc(uint32_t thr8) { return 0x80008000u - thr8 * 0x10001u; }
+template <int HI>
+__device__ __forceinline__ uint32_t drop_keep_mask2(uint32_t w, uint32_t tgc) {
+  const uint32_t x = HI ? prmt<0x4342u>(w, 0u) : prmt<0x4140u>(w, 0u);
+  return prmt<0xBB99u>(x + tgc, 0u);
 }
 // pair masks for the 16 elements of one group: mk[j] covers elements (2j, 2j+1); one Philox call
 __device__ __forceinline__ void drop_keep_masks16(const DropCfg& c, unsigned long long e, uint32_t (&mk)[8]) {
   uint32_t w[4];
   drop_bits16(c, e >> 4, w);
-  const uint32_t tg2 = drop_thr8(c, e >> 4) * 0x10001u;
+  const uint32_t tgc = drop_tgc(drop_thr8(c, e >> 4));
 #pragma unroll
-  for (int j = 0; j < 8; ++j) mk[j] = drop_keep_mask2(w[j >> 1], j & 1, tg2);
+  for (int j = 0; j < 4; ++j) {
+    mk[2 * j] = drop_keep_mask2<0>(w[j], tgc);
+    mk[2 * j + 1] = drop_keep_mask2<1>(w[j], tgc);
+  }
 }
 
 // Attention-probability dropout (the N x N site) element index: row-major over (b, h, q, k) with the k extent

@@ -210,7 +210,7 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
           uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0;
           if (kDrop) {
             drop_bits16(drop, g0 + c2 * 2 + g, w);
-            tg2 = drop_thr8(drop, g0 + c2 * 2 + g) * 0x10001u;
+            tg2 = drop_tgc(drop_thr8(drop, g0 + c2 * 2 + g));
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -222,8 +222,8 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
             rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
             uint32_t v01 = pack_bf16(p0, p1), v23 = pack_bf16(p2, p3);
             if (kDrop) {
-              v01 &= drop_keep_mask2(w[u], 0, tg2);
-              v23 &= drop_keep_mask2(w[u], 1, tg2);
+              v01 &= drop_keep_mask2<0>(w[u], tg2);
+              v23 &= drop_keep_mask2<1>(w[u], tg2);
             }
             pk[g * 8 + u * 2] = v01;
             pk[g * 8 + u * 2 + 1] = v23;

@@ -295,7 +295,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (kDrop) {  // this thread's 16 keys are exactly one Philox group (common.cuh)
           const unsigned long long grp = (rowe >> 4) + (unsigned long long)(hf * 4 + chunk);
           drop_bits16(drop, grp, w);
-          tg2 = drop_thr8(drop, grp) * 0x10001u;
+          tg2 = drop_tgc(drop_thr8(drop, grp));
         }
 #pragma unroll
         for (int t = 0; t < 8; ++t) {  // element pairs (2t, 2t+1)
@@ -304,7 +304,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           const float a0 = fmaf(__uint_as_float(dp[2 * t]), scale, negDq);
           const float a1 = fmaf(__uint_as_float(dp[2 * t + 1]), scale, negDq);
           if (kDrop) {
-            const uint32_t m = drop_keep_mask2(w[t >> 1], t & 1, tg2);
+            const uint32_t m = (t & 1) ? drop_keep_mask2<1>(w[t >> 1], tg2) : drop_keep_mask2<0>(w[t >> 1], tg2);
             const uint32_t kept = pack_bf16(p0 * a0, p1 * a1), dropped = pack_bf16(p0 * negDq, p1 * negDq);
             pk[t] = pack_bf16(p0, p1) & m;
             dk[t] = (kept & m) | (dropped & ~m);
