@@ -279,7 +279,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       const uint32_t aDSbuf = smem_u32(sDS) + (uint32_t)(i & 1) * kPBytes;
       const unsigned long long rowe = attn_drop_row_base(b, H, h, N, q < N ? q : 0) + (unsigned long long)kv0;
-#pragma unroll 1
+#pragma unroll
       for (int hf = 0; hf < 2; ++hf) {  // key halves; 16 keys per thread per half keep the live register set small
         uint32_t sv[16], dp[16];
         mbar_wait(&sm->s_full[hf], (uint32_t)i & 1u);
