@@ -262,6 +262,35 @@ def test_attention_fwd_bwd(engine, dtype, tag, Bsz, N, H, hd):
         assert rel_err(got[:, i], g[:, i]) < tol, f"d{nm}"
 
 
+@pytest.mark.parametrize("Bsz,N,H", [(2, 300, 2), (1, 2049, 1), (3, 130, 6), (2, 17, 1)])
+def test_attention_dropout_mask_is_the_same_function_in_every_kernel(Bsz, N, H):
+    """The dropout mask is a pure function of (seed, site, b, h, q, k).  The tcgen05 forward and backward kernels
+    index it by tile / key half / 16-key group, the SIMT kernels element by element: with the same descriptor all
+    four must realise the same mask, so outputs and gradients agree to bf16 accuracy.  A mask that was shifted by
+    one group in one kernel would pass every statistical test and fail this one."""
+    hd, p = 64, 0.3
+    D = H * hd
+    drop = (424242, 9, p)
+    qkv = _rand((Bsz * N, 3 * D), L.BF16, 80, 0.7)
+    dout = _rand((Bsz * N, D), L.BF16, 81)
+    res = {}
+    for eng in (L.ENGINE_SIMT, L.ENGINE_TCGEN05):
+        out = torch.empty((Bsz * N, D), dtype=torch.bfloat16, device=DEV)
+        lse = torch.empty((Bsz, H, N), device=DEV)
+        ops.attn_fwd(eng, L.BF16, qkv, out, lse, Bsz, N, H, hd, drop)
+        dqkv = torch.empty_like(qkv)
+        ops.attn_bwd(eng, L.BF16, qkv, out, dout, lse, dqkv, Bsz, N, H, hd, drop)
+        res[eng] = (out.float(), lse.clone(), dqkv.float())
+    a, b = res[L.ENGINE_SIMT], res[L.ENGINE_TCGEN05]
+    assert rel_err(b[0], a[0]) < 1e-2          # a different mask at p = 0.3 would give O(0.5)
+    assert rel_err(b[1], a[1]) < 1e-3
+    assert rel_err(b[2], a[2]) < 2e-2
+    # and the mask really is there: without dropout the outputs differ grossly
+    out0 = torch.empty((Bsz * N, D), dtype=torch.bfloat16, device=DEV)
+    ops.attn_fwd(L.ENGINE_TCGEN05, L.BF16, qkv, out0, torch.empty((Bsz, H, N), device=DEV), Bsz, N, H, hd)
+    assert rel_err(b[0], out0.float()) > 0.1
+
+
 @pytest.mark.parametrize("engine,dtype,tag", ATTN_ENGINES, ids=[e[2] for e in ATTN_ENGINES])
 def test_attention_dropout_consistency(engine, dtype, tag):
     """With dropout the mask cannot match torch's Philox stream; check keep-rate, 1/(1-p) scaling and
