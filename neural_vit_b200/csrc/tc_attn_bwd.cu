@@ -37,7 +37,7 @@ constexpr int kSoftmaxWarps = 16;
 constexpr int kQStages = 3;  // Q / dO tiles in flight
 struct AttnBwdSmem {
   uint64_t kv_full, qdo_full[kQStages], qdo_empty[kQStages], s_full[2], s_free[2], p_full, p_free, ds_free[2], dq_full,
-      dq_free;
+      dq_free, tds_free;
   uint32_t tmem_base;
 };
 
@@ -109,6 +109,12 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sDS = sP + kPBytes;                       // dS, same layout, buffer u (= tile parity) at +u*32K
   AttnBwdSmem* sm = reinterpret_cast<AttnBwdSmem*>(sDS + 2 * kPBytes);
 
+  // dQ_i = dS K_j with A = dS read from TMEM (a bf16 copy written by the softmax warps into the 64 spare columns)
+  // instead of from the K-major smem tile: -12 % shared-memory traffic per tile pair, at the price of a single-
+  // buffered TMEM operand that must be free again before the next tile's first half is written.  With dropout the
+  // softmax halves are long enough to hide that (7.9 -> 7.7 ms per launch); without dropout they are not (6.0 ->
+  // 6.6 ms), so the variant is tied to the dropout instantiation.
+  constexpr bool kTsDq = kDrop;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -129,6 +135,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     mbar_init(&sm->p_full, kSoftmaxWarps);
     mbar_init(&sm->p_free, 1);
+    mbar_init(&sm->tds_free, 1);
     mbar_init(&sm->dq_full, 1);
     mbar_init(&sm->dq_free, 128);
     fence_barrier_init();
@@ -142,6 +149,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
   const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+  const uint32_t tDS = tmem + 448;  // dS as bf16 [128 q lanes x 128 keys] = 64 columns: A operand of the dQ MMA
 
   // Role code below is warp-uniform (all 32 lanes run the loops and the barrier waits); only the TMA / MMA /
   // commit instructions themselves are predicated on one elected lane.  Issuing them from divergent code
@@ -225,6 +233,28 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         tc_commit(&sm->p_free);  // sP may be overwritten by tile i+1
       }
       __syncwarp();
+      auto issue_dq = [&]() {
+        if (i > 0) {
+          mbar_wait(&sm->dq_free, (uint32_t)(i - 1) & 1u);  // drain warps have read dQ_{i-1}
+          tc_fence_after();
+        }
+        if (elect_one()) {
+          // reduction over the 128 keys, B = K_j MN-major; A = dS from TMEM (8 columns per 16 keys) or from the
+          // K-major smem tile (two 64-key blocks 16 KB apart)
+#pragma unroll
+          for (int k = 0; k < kTileB / 16; ++k) {
+            if (kTsDq)
+              umma_ts(tDQ, tDS + k * 8, umma_desc(dKm + 128 * k, kHi), idesc_q, k > 0 ? 1u : 0u);
+            else
+              umma_ss(tDQ, umma_desc(dDS + (k >> 2) * (16384 >> 4) + (k & 3) * 2, kHi), umma_desc(dKm + 128 * k, kHi),
+                      idesc_q, k > 0 ? 1u : 0u);
+          }
+          tc_commit(&sm->dq_full);
+          if (kTsDq) tc_commit(&sm->tds_free);
+        }
+        __syncwarp();
+      };
+      if (kTsDq) issue_dq();  // second, so that the TMEM copy of dS is free before tile i+1's first half is written
       if (more) {
         mbar_wait(&sm->s_free[1], (uint32_t)i & 1u);
         tc_fence_after();
@@ -234,23 +264,20 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
         for (int k = 0; k < kTileB / 16; ++k)
           umma_ss(tDK, umma_desc(dDSm + 128 * k, kHi), umma_desc(dQm + 128 * k, kHi), idesc_t, k > 0 ? 1u : accum);
+        if (kTsDq) {
+          tc_commit(&sm->qdo_empty[st]);
+          tc_commit(&sm->ds_free[i & 1]);
+        }
       }
       __syncwarp();
-      if (i > 0) {
-        mbar_wait(&sm->dq_free, (uint32_t)(i - 1) & 1u);  // drain warps have read dQ_{i-1}
-        tc_fence_after();
+      if (!kTsDq) {
+        issue_dq();
+        if (elect_one()) {
+          tc_commit(&sm->qdo_empty[st]);
+          tc_commit(&sm->ds_free[i & 1]);
+        }
+        __syncwarp();
       }
-      if (elect_one()) {
-        // reduction over the 128 keys: sDS K-major (two 64-key blocks 16 KB apart), K_j MN-major
-#pragma unroll
-        for (int k = 0; k < kTileB / 16; ++k)
-          umma_ss(tDQ, umma_desc(dDS + (k >> 2) * (16384 >> 4) + (k & 3) * 2, kHi), umma_desc(dKm + 128 * k, kHi),
-                  idesc_q, k > 0 ? 1u : 0u);
-        tc_commit(&sm->qdo_empty[st]);
-        tc_commit(&sm->dq_full);
-        tc_commit(&sm->ds_free[i & 1]);
-      }
-      __syncwarp();
       st = stn;
     }
   } else if (warp < kSoftmaxWarps) {
@@ -314,9 +341,11 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           }
         }
         if (hf == 0) {
+          if (kTsDq && i >= 1) mbar_wait(&sm->tds_free, (uint32_t)(i - 1) & 1u);  // dQ_{i-1} has read tDS
           if (i >= 1) mbar_wait(&sm->p_free, (uint32_t)(i - 1) & 1u);  // dV_{i-1} has read sP
           if (i >= 2) mbar_wait(&sm->ds_free[i & 1], (((uint32_t)i >> 1) - 1u) & 1u);  // tile i-2 has read this sDS
         }
+        if (kTsDq) tmem_st8(tDS + lane_off + hf * 32 + chunk * 8, dk);  // dS for the dQ MMA (A operand from TMEM)
         // row r of 64-key block hf: 16-byte pieces chunk * 2 + g, XOR-swizzled with (r & 7)
         const uint32_t row_off = (uint32_t)hf * 16384u + (uint32_t)r * 128u;
 #pragma unroll
@@ -325,6 +354,10 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           st_shared_v4(smem_u32(sP) + row_off + piece, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           st_shared_v4(aDSbuf + row_off + piece, dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
         }
+      }
+      if (kTsDq) {
+        tmem_st_wait();
+        tc_fence_before();
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
