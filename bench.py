@@ -113,16 +113,21 @@ class ClockSampler:
 
 def ncu_traffic_bytes(batch, args):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
-    capture (profiles/r1_ncu_attn_B256_dropout.json); only valid for the shape it was captured on."""
+    capture of the final build (profiles/r1_ncu_attn_final_B256_dropout.json, written by tools/ncu_summary.py); only
+    valid for the shape it was captured on."""
     if (batch, args.layers, args.embed_dim, args.trials, args.time) != (256, 8, 384, 8, 256):
         return None
-    path = os.path.join(ROOT, "profiles", "r1_ncu_attn_B256_dropout.json")
+    path = os.path.join(ROOT, "profiles", "r1_ncu_attn_final_B256_dropout.json")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
     try:
         with open(path) as fh:
-            k = json.load(fh)["void tc_attn_bwd_kernel<1>"]
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-        return sum(float(k[m][0]) * scale[k[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    except (OSError, KeyError, ValueError):
+            k = next(e for e in json.load(fh) if "tc_attn_bwd_kernel<1>" in e["kernel"])
+        total = 0.0
+        for m in ("dram_rd", "dram_wr"):
+            v, u = k[m].split()
+            total += float(v) * scale[u]
+        return total
+    except (OSError, KeyError, ValueError, StopIteration):
         return None
 
 
