@@ -386,6 +386,18 @@ def test_dropout_mask_matches_numpy_oracle(seed, site, p):
     assert torch.equal(gp != 0, ref)
     kept = gp[ref]
     assert torch.allclose(kept, torch.full_like(kept, R.inv_keep(p)), rtol=1e-6)
+    # LayerNorm backward's fused branch-gradient output (quad-shared Philox words): dy = 0 -> dx = g_res = 1
+    for dt in (L.F32, L.BF16):
+        td = ops.torch_dtype(dt)
+        dy0 = torch.zeros((rows, D), dtype=td, device=DEV)
+        xln = torch.randn((rows, D), device=DEV)
+        mean, rstd = torch.zeros(rows, device=DEV), torch.ones(rows, device=DEV)
+        dx = torch.empty((rows, D), device=DEV)
+        gpl = torch.empty((rows, D), dtype=td, device=DEV)
+        ops.ln_bwd(dy0, dt, xln, D, mean, rstd, torch.ones(D, device=DEV), g, dx, D, torch.zeros(D, device=DEV),
+                   torch.zeros(D, device=DEV), rows, D, gp=gpl, row_scale=None, rows_per_group=1,
+                   drop=(seed, site, p), gp_colsum=torch.zeros(D, device=DEV))
+        assert torch.equal(gpl != 0, ref), dt
     # tcgen05 GEMM epilogues: zero operands, bias 1 -> the output is the mask times a constant
     a = torch.zeros((rows, 64), dtype=torch.bfloat16, device=DEV)
     b = torch.zeros((D, 64), dtype=torch.bfloat16, device=DEV)
