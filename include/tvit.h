@@ -77,7 +77,10 @@ enum {
   TVIT_EPI_ACCUM_F32 = 4,
   /* row m = b * n_patches + i;  out_f32[(b*(n_patches+1) + 1 + i), n] =
    *   dropout(acc + bias[n] + pos_k[k'][n] + pos_f[f'][n] + pos_t[t'][n])        (:300-313) */
-  TVIT_EPI_PATCH_EMBED = 5
+  TVIT_EPI_PATCH_EMBED = 5,
+  /* out_f32[m,n] = exp(alpha * acc - row_scale[m])  with row_scale = the row log-sum-exp of tvit_attn_fwd:
+   * materialised softmax(q k^T * alpha) tile by tile on the tensor cores (get_attention_maps, model.py:325-350) */
+  TVIT_EPI_SOFTMAX_PROBS = 6
 };
 
 typedef struct {
@@ -106,6 +109,7 @@ typedef struct {
   const float* pos_t;
   int Kp, Fp, Tp;
   int split_k; /* ACCUM_F32: number of K splits, 0 = choose */
+  float alpha; /* SOFTMAX_PROBS: score scale (head_dim^-0.5) */
 } tvit_gemm_args;
 
 int tvit_gemm(const tvit_gemm_args* args, tvit_stream_t stream);
@@ -168,28 +172,57 @@ int tvit_cast_weight(const float* w, int R, int C, const float* row_scale, void*
 
 /* Finish the gradients of  z = gamma (.) (a W^T + b)  from  G = gp^T a  and  cs = colsum(gp):
  *   dW[r,c] = gamma[r] * G[r,c];  dgamma[r] = sum_c W[r,c] G[r,c] + b[r] cs[r];  db[r] = gamma[r] cs[r].
- * gamma == NULL means no LayerScale (dW = G, db = cs, dgamma untouched).  (model.py:74-82 backward) */
+ * gamma == NULL means no LayerScale (dW = G, db = cs, dgamma untouched).  (model.py:74-82 backward)
+ * accumulate != 0: the three outputs are added to (gradient buffers that several backward passes accumulate into,
+ * e.g. the flat all-reduce buckets) instead of overwritten. */
 int tvit_ls_finalize(const float* G, const float* W, const float* gamma, const float* bias, const float* cs,
-                     float* dW, float* dgamma, float* dbias, int R, int C, tvit_stream_t stream);
+                     float* dW, float* dgamma, float* dbias, int R, int C, int accumulate, tvit_stream_t stream);
 
 /* h[b,0,:] = dropout(cls[:])  -- CLS prepend (model.py:309-313); element index = (b*N)*D + c. */
 int tvit_cls_rows(const float* cls, float* h, int B, int N, int D, const tvit_dropout* drop, tvit_stream_t stream);
 
 /* Backward of embed: g0 fp32 [B, n+1, D] (gradient of the residual stream at block 0's input)
  *   gtok[T][b*n + i, :] = g0[b, 1+i, :] * dropout_mult      (input of the patch-embed weight-gradient GEMM)
- *   R[i,:] = sum_b of the same (fp32)   dcls[:] = sum_b g0[b,0,:] * dropout_mult
+ *   R[i,:] = sum_b of the same (fp32)   dcls[:] (+)= sum_b g0[b,0,:] * dropout_mult
+ * (accumulate != 0: dcls and the four outputs of tvit_pos_grad_reduce are added to instead of overwritten)
  * then tvit_pos_grad_reduce folds R [n, D] into dpos_k [Kp,D], dpos_f [Fp,D], dpos_t [Tp,D] and dbias [D]. */
 int tvit_embed_bwd_prep(const float* g0, int B, int n, int D, const tvit_dropout* drop, void* gtok, int dtype,
-                        float* R, float* dcls, tvit_stream_t stream);
+                        float* R, float* dcls, int accumulate, tvit_stream_t stream);
 int tvit_pos_grad_reduce(const float* R, int Kp, int Fp, int Tp, int D, float* dpos_k, float* dpos_f,
-                         float* dpos_t, float* dbias, tvit_stream_t stream);
+                         float* dpos_t, float* dbias, int accumulate, tvit_stream_t stream);
 
 /* y = x + alpha * y  style helpers are intentionally absent: everything else is fused above. */
 
-/* Fused AdamW step (torch.optim.AdamW semantics, train.py:154-156,227) over one flat
- * fp32 parameter/gradient/moment range. step is 1-based. */
-int tvit_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-               float eps, float weight_decay, int step, float grad_scale, tvit_stream_t stream);
+/* Fused AdamW step (torch.optim.AdamW semantics, train.py:154-156,227) over one flat fp32
+ * parameter/gradient/moment range; step is 1-based.  If shadow_bf16 != NULL the updated parameters are also written
+ * there as bf16 (the forward operand copies of the tensor-core path: no separate cast pass after the update). */
+int tvit_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, float grad_scale, tvit_stream_t stream);
+
+/* One launch that rebuilds the transposed operand shadows out_t[c,r] = row_scale[r] * w[r,c] (row_scale = LayerScale
+ * gamma or NULL) of every Linear weight listed in a DEVICE-resident descriptor table; tile_begin is the prefix sum of
+ * ceil(R/32)*ceil(C/32) over the table and total_tiles its total. */
+typedef struct {
+  const float* w;
+  const float* row_scale;
+  void* out_t;
+  int R, C;
+  int tile_begin;
+  int tiles_x; /* ceil(C / 32) */
+} tvit_shadow_desc;
+int tvit_shadow_t_multi(const tvit_shadow_desc* descs_device, int count, int total_tiles, int dtype,
+                        tvit_stream_t stream);
+
+/* Class-weighted, label-smoothed cross entropy (torch.nn.CrossEntropyLoss(weight, label_smoothing), mean reduction;
+ * train.py:167-170,225) forward AND backward in one launch, plus on-device running metrics so the loop needs no host
+ * synchronisation per step (train.py:229-235, evaluate :77-105):
+ *   loss[0] = the batch loss; dlogits[B,C] = d loss / d logits (NULL in evaluation);
+ *   metric_acc[0] += loss * B, metric_acc[1] += #(argmax == label), metric_acc[2] += B   (NULL to skip)
+ *   prob_out[i] = softmax(logits_i)[1], label_out[i] = label_i  (NULL to skip; inputs of the epoch-end AUC).
+ * labels are int64; class_weight may be NULL. */
+int tvit_ce_loss(const float* logits, const long long* labels, const float* class_weight, float label_smoothing,
+                 int B, int C, float* loss, float* dlogits, float* metric_acc, float* prob_out, float* label_out,
+                 tvit_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libtvit_b200.so")
 
 F32, BF16 = 0, 1
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
-EPI_STORE, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_GELU_BWD, EPI_ACCUM_F32, EPI_PATCH_EMBED = range(6)
+EPI_STORE, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_GELU_BWD, EPI_ACCUM_F32, EPI_PATCH_EMBED, EPI_SOFTMAX_PROBS = range(7)
 
 c_void_p, c_int, c_float, c_ll, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
                                              ctypes.c_longlong, ctypes.c_size_t)
@@ -35,8 +35,14 @@ class GemmArgs(ctypes.Structure):
         ("resid", c_void_p), ("ldres", c_ll), ("gamma", c_void_p), ("row_scale", c_void_p),
         ("rows_per_group", c_int), ("drop", Dropout),
         ("pos_k", c_void_p), ("pos_f", c_void_p), ("pos_t", c_void_p),
-        ("Kp", c_int), ("Fp", c_int), ("Tp", c_int), ("split_k", c_int),
+        ("Kp", c_int), ("Fp", c_int), ("Tp", c_int), ("split_k", c_int), ("alpha", c_float),
     ]
+
+
+class ShadowDesc(ctypes.Structure):
+    """tvit_shadow_desc (include/tvit.h): one row of the device-resident table of tvit_shadow_t_multi."""
+    _fields_ = [("w", c_void_p), ("row_scale", c_void_p), ("out_t", c_void_p), ("R", c_int), ("C", c_int),
+                ("tile_begin", c_int), ("tiles_x", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/tvit.h declares
@@ -61,14 +67,17 @@ SIGNATURES = {
                                       c_int, c_void_p, c_void_p]),
     "tvit_colsum": (c_int, [c_void_p, c_int, c_ll, c_int, c_ll, c_void_p, c_void_p]),
     "tvit_cast_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    "tvit_ls_finalize": (c_int, [c_void_p] * 8 + [c_int, c_int, c_void_p]),
+    "tvit_ls_finalize": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p]),
     "tvit_cls_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(Dropout), c_void_p]),
     "tvit_embed_bwd_prep": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(Dropout), c_void_p, c_int,
-                                    c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_int, c_void_p]),
     "tvit_pos_grad_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p]),
-    "tvit_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
-                           c_int, c_float, c_void_p]),
+                                     c_int, c_void_p]),
+    "tvit_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float,
+                           c_float, c_int, c_float, c_void_p]),
+    "tvit_shadow_t_multi": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tvit_ce_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -84,6 +84,9 @@ extern "C" int tvit_gemm(const tvit_gemm_args* a, tvit_stream_t stream) {
                      "gemm: PATCH_EMBED needs positional tables");
       TVIT_CHECK_ARG(a->M % (a->Kp * a->Fp * a->Tp) == 0, "gemm: PATCH_EMBED M must be B * n_patches");
       break;
+    case TVIT_EPI_SOFTMAX_PROBS:
+      TVIT_CHECK_ARG(a->row_scale != nullptr, "gemm: SOFTMAX_PROBS needs the row log-sum-exp in row_scale");
+      break;
     default:
       break;
   }

@@ -1,7 +1,7 @@
 // Bandwidth-bound kernels of the Temporal 3D ViT hot path (sm_100a):
 // tubelet im2col + cast, LayerNorm fwd/bwd (warp-shuffle reductions, 16-byte accesses), residual-branch
 // gradient preparation, bias-gradient column sums, weight shadows, LayerScale gradient finalisation,
-// CLS / positional-embedding gradients and a fused AdamW step.
+// CLS / positional-embedding gradients.  (AdamW, multi-tensor shadows and the loss kernel: optim_loss.cu)
 //
 // Each kernel is HBM-bound; the algorithmic bytes per element are listed in DESIGN.md section 4.
 #include "common.cuh"
@@ -307,14 +307,15 @@ __global__ void cast_weight_kernel(const float* __restrict__ w, int R, int C, co
 __global__ void ls_finalize_kernel(const float* __restrict__ G, const float* __restrict__ W,
                                    const float* __restrict__ gamma, const float* __restrict__ bias,
                                    const float* __restrict__ cs, float* __restrict__ dW, float* __restrict__ dgamma,
-                                   float* __restrict__ dbias, int R, int C) {
+                                   float* __restrict__ dbias, int R, int C, int accumulate) {
   __shared__ float part[32];
   const int r = blockIdx.x;
   const float gm = gamma ? gamma[r] : 1.0f;
   float s = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float gv = G[(long long)r * C + c];
-    dW[(long long)r * C + c] = gm * gv;
+    float* d = dW + (long long)r * C + c;
+    *d = accumulate ? *d + gm * gv : gm * gv;
     if (gamma) s += W[(long long)r * C + c] * gv;
   }
   s = warp_sum(s);
@@ -324,8 +325,8 @@ __global__ void ls_finalize_kernel(const float* __restrict__ G, const float* __r
     float t = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
     const float c = cs[r];
-    if (gamma && dgamma) dgamma[r] = t + (bias ? bias[r] : 0.f) * c;
-    if (dbias) dbias[r] = gm * c;
+    if (gamma && dgamma) dgamma[r] = (accumulate ? dgamma[r] : 0.f) + t + (bias ? bias[r] : 0.f) * c;
+    if (dbias) dbias[r] = (accumulate ? dbias[r] : 0.f) + gm * c;
   }
 }
 
@@ -340,7 +341,8 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls, float* __restrict
 // block (i, vector-column chunk): i in [0, n] ; i == n handles the CLS row
 template <typename T>
 __global__ void embed_bwd_prep_kernel(const float* __restrict__ g0, int B, int n, int D, DropCfg drop,
-                                      T* __restrict__ gtok, float* __restrict__ R, float* __restrict__ dcls) {
+                                      T* __restrict__ gtok, float* __restrict__ R, float* __restrict__ dcls,
+                                      int accumulate) {
   const int nvec = D >> 2;
   const int vc = blockIdx.y * blockDim.x + threadIdx.x;
   if (vc >= nvec) return;
@@ -358,49 +360,37 @@ __global__ void embed_bwd_prep_kernel(const float* __restrict__ g0, int B, int n
     acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
   }
   float* dst = (i == n) ? dcls : (R + (long long)i * D);
+  if (i == n && accumulate) {
+    const float4 o = ld4(dst + 4 * vc);
+    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+  }
   st4(dst + 4 * vc, acc);
 }
 
 // block r in [0, Kp+Fp+Tp]: one table row (or the bias row when r == Kp+Fp+Tp)
 __global__ void pos_grad_reduce_kernel(const float* __restrict__ R, int Kp, int Fp, int Tp, int D,
                                        float* __restrict__ dpk, float* __restrict__ dpf, float* __restrict__ dpt,
-                                       float* __restrict__ dbias) {
+                                       float* __restrict__ dbias, int accumulate) {
   const int r = blockIdx.x;
   const int n = Kp * Fp * Tp;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float s = 0.f;
     if (r < Kp) {
       for (int j = 0; j < Fp * Tp; ++j) s += R[((long long)r * Fp * Tp + j) * D + c];
-      dpk[(long long)r * D + c] = s;
+      dpk[(long long)r * D + c] = accumulate ? dpk[(long long)r * D + c] + s : s;
     } else if (r < Kp + Fp) {
       const int f = r - Kp;
       for (int k = 0; k < Kp; ++k)
         for (int t = 0; t < Tp; ++t) s += R[(((long long)k * Fp + f) * Tp + t) * D + c];
-      dpf[(long long)f * D + c] = s;
+      dpf[(long long)f * D + c] = accumulate ? dpf[(long long)f * D + c] + s : s;
     } else if (r < Kp + Fp + Tp) {
       const int t = r - Kp - Fp;
       for (int j = 0; j < Kp * Fp; ++j) s += R[((long long)j * Tp + t) * D + c];
-      dpt[(long long)t * D + c] = s;
+      dpt[(long long)t * D + c] = accumulate ? dpt[(long long)t * D + c] + s : s;
     } else {
       for (int j = 0; j < n; ++j) s += R[(long long)j * D + c];
-      dbias[c] = s;
+      dbias[c] = accumulate ? dbias[c] + s : s;
     }
-  }
-}
-
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
-                             float bc1, float bc2_sqrt, float gscale) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * gscale;
-    float pi = p[i] * (1.0f - lr * wd);
-    const float mi = b1 * m[i] + (1.0f - b1) * gi;
-    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= (lr / bc1) * (mi / denom);
-    p[i] = pi;
   }
 }
 
@@ -616,10 +606,11 @@ extern "C" int tvit_cast_weight(const float* w, int R, int C, const float* row_s
 }
 
 extern "C" int tvit_ls_finalize(const float* G, const float* W, const float* gamma, const float* bias, const float* cs,
-                                float* dW, float* dgamma, float* dbias, int R, int C, tvit_stream_t stream) {
+                                float* dW, float* dgamma, float* dbias, int R, int C, int accumulate,
+                                tvit_stream_t stream) {
   TVIT_CHECK_ARG(G && cs && dW, "ls_finalize: null pointer");
   TVIT_CHECK_ARG(!gamma || W, "ls_finalize: W required with gamma");
-  ls_finalize_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(G, W, gamma, bias, cs, dW, dgamma, dbias, R, C);
+  ls_finalize_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(G, W, gamma, bias, cs, dW, dgamma, dbias, R, C, accumulate);
   TVIT_LAUNCH_OK();
   return TVIT_OK;
 }
@@ -634,7 +625,7 @@ extern "C" int tvit_cls_rows(const float* cls, float* h, int B, int N, int D, co
 }
 
 extern "C" int tvit_embed_bwd_prep(const float* g0, int B, int n, int D, const tvit_dropout* drop, void* gtok,
-                                   int dtype, float* R, float* dcls, tvit_stream_t stream) {
+                                   int dtype, float* R, float* dcls, int accumulate, tvit_stream_t stream) {
   TVIT_CHECK_ARG(g0 && gtok && R && dcls, "embed_bwd_prep: null pointer");
   TVIT_CHECK_ARG(D % 4 == 0, "embed_bwd_prep: D must be a multiple of 4");
   const int nvec = D / 4;
@@ -642,30 +633,17 @@ extern "C" int tvit_embed_bwd_prep(const float* g0, int B, int n, int D, const t
   dim3 grid(n + 1, (nvec + bx - 1) / bx);
   const DropCfg dc = make_drop(drop);
   DISPATCH_T(dtype, {
-    embed_bwd_prep_kernel<T><<<grid, bx, 0, (cudaStream_t)stream>>>(g0, B, n, D, dc, (T*)gtok, R, dcls);
+    embed_bwd_prep_kernel<T><<<grid, bx, 0, (cudaStream_t)stream>>>(g0, B, n, D, dc, (T*)gtok, R, dcls, accumulate);
   })
   TVIT_LAUNCH_OK();
   return TVIT_OK;
 }
 
 extern "C" int tvit_pos_grad_reduce(const float* R, int Kp, int Fp, int Tp, int D, float* dpos_k, float* dpos_f,
-                                    float* dpos_t, float* dbias, tvit_stream_t stream) {
+                                    float* dpos_t, float* dbias, int accumulate, tvit_stream_t stream) {
   TVIT_CHECK_ARG(R && dpos_k && dpos_f && dpos_t && dbias, "pos_grad_reduce: null pointer");
   pos_grad_reduce_kernel<<<Kp + Fp + Tp + 1, 128, 0, (cudaStream_t)stream>>>(R, Kp, Fp, Tp, D, dpos_k, dpos_f, dpos_t,
-                                                                           dbias);
-  TVIT_LAUNCH_OK();
-  return TVIT_OK;
-}
-
-extern "C" int tvit_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                          float eps, float weight_decay, int step, float grad_scale, tvit_stream_t stream) {
-  TVIT_CHECK_ARG(p && g && m && v && step >= 1, "adamw: bad argument");
-  if (n == 0) return TVIT_OK;
-  const float bc1 = 1.0f - powf(beta1, (float)step);
-  const float bc2 = sqrtf(1.0f - powf(beta2, (float)step));
-  const int grid = blocks_for(n, 256 * 4, num_sms() * 8);
-  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
-                                                       grad_scale);
+                                                                           dbias, accumulate);
   TVIT_LAUNCH_OK();
   return TVIT_OK;
 }

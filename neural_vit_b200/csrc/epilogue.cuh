@@ -22,6 +22,7 @@ struct EpiParams {
   const float* pos_f;
   const float* pos_t;
   int Kp, Fp, Tp;
+  float alpha;  // SOFTMAX_PROBS score scale
   int vec_ok;   // N % 4 == 0 and every leading dimension % 4 == 0 -> 4-wide vector path is legal
   int vec8_ok;  // same with 8 (16-byte bf16 accesses)
   int vec16_ok; // N, leading dimensions % 16 == 0 and 32-byte aligned bases: 256-bit (full-sector) accesses
@@ -48,6 +49,7 @@ inline EpiParams make_epi_params(const tvit_gemm_args* a) {
   p.Kp = a->Kp;
   p.Fp = a->Fp;
   p.Tp = a->Tp;
+  p.alpha = a->alpha;
   p.vec_ok = (a->N % 4 == 0) && (a->ldo % 4 == 0) && (a->aux == nullptr || a->ldaux % 4 == 0) &&
              (a->resid == nullptr || a->ldres % 4 == 0);
   p.vec8_ok = (a->N % 8 == 0) && (a->ldo % 8 == 0) && (a->aux == nullptr || a->ldaux % 8 == 0);
@@ -109,6 +111,8 @@ __device__ __forceinline__ void epi_apply1(const EpiParams& p, int m, int n, flo
     Act<T>::st((T*)p.out + m * p.ldo + n, v * drop_mult(p.drop, (unsigned long long)m * p.N + n) * gelu_grad_t<T>(h));
   } else if (EPI == TVIT_EPI_ACCUM_F32) {
     atomicAdd((float*)p.out + m * p.ldo + n, v);
+  } else if (EPI == TVIT_EPI_SOFTMAX_PROBS) {
+    ((float*)p.out)[m * p.ldo + n] = __expf(fmaf(v, p.alpha, -p.row_scale[m]));
   } else if (EPI == TVIT_EPI_PATCH_EMBED) {
     const int npatch = p.Kp * p.Fp * p.Tp;
     const int b = m / npatch, i = m - b * npatch;
@@ -170,6 +174,10 @@ __device__ __forceinline__ void epi_apply4(const EpiParams& p, int m, int n0, fl
   } else if (EPI == TVIT_EPI_ACCUM_F32) {
     float* o = (float*)p.out + m * p.ldo + n0;
     atomicAdd(o + 0, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+  } else if (EPI == TVIT_EPI_SOFTMAX_PROBS) {
+    const float l = p.row_scale[m];
+    st4((float*)p.out + m * p.ldo + n0, make_float4(__expf(fmaf(v.x, p.alpha, -l)), __expf(fmaf(v.y, p.alpha, -l)),
+                                                     __expf(fmaf(v.z, p.alpha, -l)), __expf(fmaf(v.w, p.alpha, -l))));
   } else if (EPI == TVIT_EPI_PATCH_EMBED) {
     const int npatch = p.Kp * p.Fp * p.Tp;
     const int b = m / npatch, i = m - b * npatch;

@@ -80,6 +80,7 @@ static int launch_simt_gemm(const tvit_gemm_args* a, cudaStream_t s) {
     LAUNCH(TVIT_EPI_GELU_BWD)
     LAUNCH(TVIT_EPI_ACCUM_F32)
     LAUNCH(TVIT_EPI_PATCH_EMBED)
+    LAUNCH(TVIT_EPI_SOFTMAX_PROBS)
     default:
       return fail(TVIT_ERR_BAD_ARG, "gemm: unknown epilogue %d", a->epilogue);
   }

@@ -285,18 +285,11 @@ int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int
   const int D = H * hd;
   if (D % 8 != 0) return fail(TVIT_ERR_BAD_ARG, "attention: embed dim must be a multiple of 8");
   constexpr int smem_bytes = 5 * kTileBytes + 1024 + 256 + 2048;  // tiles + alignment + barriers + partner exchange
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(tc_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(tc_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  });
-  if (attr_err != cudaSuccess)
-    return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  int rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_fwd_kernel<false>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_fwd_kernel<true>, smem_bytes)) != TVIT_OK) return rc;
   CUtensorMap tm;
-  int rc = make_qkv_tmap(&tm, qkv, B, N, 3 * D, kTile);
-  if (rc != TVIT_OK) return rc;
+  if ((rc = make_qkv_tmap(&tm, qkv, B, N, 3 * D, kTile)) != TVIT_OK) return rc;
   dim3 grid((N + kTile - 1) / kTile, H, B);
   const float scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
   const DropCfg dc = make_drop(drop);

@@ -451,15 +451,9 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   const size_t dq_bytes = (size_t)B * H * nq * 16 * 128 * 4 * sizeof(float);
 
   constexpr int smem_bytes = 2 * kTileBytesB + kQStages * 2 * kTileBytesB + 3 * kPBytes + 1024 + 256;  // 225.25 KB
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(tc_attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(tc_attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  });
-  if (attr_err != cudaSuccess)
-    return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  int rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true>, smem_bytes)) != TVIT_OK) return rc;
 
   TVIT_CUDA_OK(cudaMemsetAsync(dqacc, 0, dq_bytes, s));
   {
@@ -469,7 +463,6 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
     TVIT_LAUNCH_OK();
   }
   CUtensorMap tm_qkv, tm_do;
-  int rc;
   if ((rc = make_tok_tmap(&tm_qkv, qkv, B, N, 3 * D)) != TVIT_OK) return rc;
   if ((rc = make_tok_tmap(&tm_do, dout, B, N, D)) != TVIT_OK) return rc;
   dim3 grid(nq, H, B);

@@ -14,6 +14,10 @@
 //   are LBO = 8192 B apart, 8-k-row groups SBO = 1024 B apart.
 // Work items = m_tile x n_tile x k_split, static round-robin over the persistent CTAs.
 #include <cstdlib>
+#include <cstring>
+#include <set>
+#include <unordered_map>
+#include <utility>
 
 #include "epilogue.cuh"
 #include "tc_common.cuh"
@@ -40,11 +44,51 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are cached, keyed by (device, base pointer, rank, dims, strides, box): activations come from
+// PyTorch's caching allocator, so from the second training step on every launch finds its descriptors here instead
+// of re-encoding them ("TMA descriptor cache keyed by ptr/shape").  A tensor map only describes
+// addresses and extents -- it never caches data -- so reuse after the allocator hands the same block to a different
+// tensor of the same geometry is correct by construction.
+struct TmapKey {
+  uint64_t v[11];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t x : k.v) h = (h ^ x) * 0x100000001b3ull;
+    return (size_t)h;
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+constexpr size_t kTmapCacheMax = 8192;  // entries (128 B each); cleared wholesale when full
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return fail(TVIT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if (((uintptr_t)base & 15u) != 0) return fail(TVIT_ERR_BAD_ARG, "TMA base address %p not 16-byte aligned", base);
+  if (rank < 1 || rank > 3) return fail(TVIT_ERR_BAD_ARG, "tensor map rank %d not in [1,3]", rank);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.v[0] = (uint64_t)(uintptr_t)base;
+  key.v[1] = ((uint64_t)(uint32_t)dev << 32) | (uint32_t)rank;
+  for (int i = 0; i < rank; ++i) {
+    key.v[2 + i] = dims[i];
+    key.v[8 + i] = box[i];
+    if (i > 0) key.v[5 + i] = strides_bytes[i - 1];
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return TVIT_OK;
+    }
+  }
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {
@@ -62,6 +106,29 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TVIT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() >= kTmapCacheMax) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
+  }
+  return TVIT_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember (kernel, device) pairs
+// so that a process driving several GPUs sets it on each of them (a process-wide once-flag left the second device
+// at the 48 KB default).
+int ensure_dynamic_smem(const void* kern, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(TVIT_ERR_CUDA, "cudaGetDevice failed: %s", cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({kern, dev})) return TVIT_OK;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess)
+    return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", bytes, cudaGetErrorString(e));
+  done.insert({kern, dev});
   return TVIT_OK;
 }
 
@@ -372,17 +439,9 @@ static int launch_tc_d(const tvit_gemm_args* a, const GemmShape& sh, const EpiPa
   using Cfg = GemmCfg<BN>;
   auto kern = tc_gemm_kernel<BN, MN, MN, EPI, kDrop, B_RES>;
   constexpr int kSmem = B_RES ? (kMaxResKBlocks * Cfg::kBBytes + 4 * Cfg::kABytes + 1024 + 256 + 8192) : Cfg::kSmemBytes;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-  });
-  if (attr_err != cudaSuccess)
-    return fail(TVIT_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", kSmem,
-                cudaGetErrorString(attr_err));
-
-  CUtensorMap tmA, tmB;
   int rc;
+  if ((rc = ensure_dynamic_smem((const void*)kern, kSmem)) != TVIT_OK) return rc;
+  CUtensorMap tmA, tmB;
   if (!MN) {
     // A [M,K] K contiguous; B [N,K] K contiguous
     const uint64_t da[2] = {(uint64_t)a->K, (uint64_t)a->M}, sa[1] = {(uint64_t)a->lda * 2};
@@ -439,6 +498,7 @@ static int dispatch_epi(const tvit_gemm_args* a, const GemmShape& sh, const EpiP
     case TVIT_EPI_GELU_BWD: return launch_tc<BN, false, TVIT_EPI_GELU_BWD>(a, sh, ep, s);
     case TVIT_EPI_PATCH_EMBED: return launch_tc<BN, false, TVIT_EPI_PATCH_EMBED>(a, sh, ep, s);
     case TVIT_EPI_ACCUM_F32: return launch_tc<BN, false, TVIT_EPI_ACCUM_F32>(a, sh, ep, s);
+    case TVIT_EPI_SOFTMAX_PROBS: return launch_tc<BN, false, TVIT_EPI_SOFTMAX_PROBS>(a, sh, ep, s);
     default: return fail(TVIT_ERR_BAD_ARG, "gemm: unknown epilogue %d", a->epilogue);
   }
 }

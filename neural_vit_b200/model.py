@@ -32,6 +32,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
+from .gradsink import GradSink
 
 
 @dataclass
@@ -95,13 +96,14 @@ class _Ctx:
     """Per-forward launch context shared by the autograd Functions (plain Python, no tensors)."""
 
     def __init__(self, engine: int, attn_engine: int, dtype: int, training: bool, seed: int,
-                 cfg: Temporal3DViTConfig):
+                 cfg: Temporal3DViTConfig, sink: Optional[GradSink] = None):
         self.engine = engine
         self.attn_engine = attn_engine
         self.dtype = dtype
         self.training = training
         self.seed = seed
         self.cfg = cfg
+        self.sink = sink      # flat gradient buffers the backward kernels accumulate into (None: autograd .grad)
 
     def drop(self, site: int, p: float):
         if not self.training or p <= 0.0:
@@ -120,27 +122,62 @@ def _zeros(shape, device):
 class _Shadows:
     """Operand copies of the Linear weights in the activation dtype:
     ``w`` [out,in] for forward, ``wt`` [in,out] (rows of w optionally pre-scaled by the LayerScale
-    gamma) for the input-gradient GEMM.  Rebuilt when the parameter (or gamma) changes."""
+    gamma) for the input-gradient GEMM.
+
+    An entry is valid while its stamp matches: parameter storage pointers, their autograd ``_version`` counters
+    and the cache ``generation``.  Every writer this package controls that updates parameters through raw pointers
+    bumps ``_version`` (``ops.adamw``, ``FusedAdamW``, the DDP broadcast); ``invalidate()`` is the explicit escape
+    hatch for anything else (``Temporal3DViT.invalidate_shadows()``).  ``adopt`` installs shadows somebody else
+    already wrote (the fused optimizer re-casts them inside its update kernel)."""
 
     def __init__(self):
         self._cache: Dict[tuple, tuple] = {}
+        self.generation = 0
+
+    def invalidate(self) -> None:
+        self.generation += 1
+
+    def _stamp(self, weight, gamma, dtype):
+        return (weight.data_ptr(), weight._version, None if gamma is None else (gamma.data_ptr(), gamma._version),
+                dtype, str(weight.device), self.generation)
+
+    def adopt(self, key, weight, gamma, dtype: int, w_sh, wt_sh) -> None:
+        self._cache[key] = (self._stamp(weight, gamma, dtype), w_sh, wt_sh)
+
+    def peek(self, key):
+        hit = self._cache.get(key)
+        return None if hit is None else (hit[1], hit[2])
 
     def get(self, key, weight: torch.Tensor, gamma: Optional[torch.Tensor], dtype: int, need_t: bool):
         w2 = weight.reshape(weight.shape[0], -1)
-        stamp = (weight.data_ptr(), weight._version, None if gamma is None else (gamma.data_ptr(), gamma._version),
-                 dtype, str(weight.device))
+        stamp = self._stamp(weight, gamma, dtype)
         hit = self._cache.get(key)
         if hit is not None and hit[0] == stamp and (hit[2] is not None or not need_t):
             return hit[1], hit[2]
         R, C = w2.shape
         td = ops.torch_dtype(dtype)
-        w_sh = w2.detach() if dtype == L.F32 else _empty((R, C), td, weight.device)
-        wt_sh = _empty((C, R), td, weight.device) if need_t else None
+        # reuse the previous buffers when only the contents are stale (keeps pointers stable for the TMA cache)
+        w_sh = wt_sh = None
+        if hit is not None and hit[0][3] == dtype and hit[0][4] == stamp[4]:
+            w_sh, wt_sh = hit[1], hit[2]
+        if dtype == L.F32:
+            w_sh = w2.detach()
+        elif w_sh is None or w_sh.shape != (R, C):
+            w_sh = _empty((R, C), td, weight.device)
+        if need_t and (wt_sh is None or wt_sh.shape != (C, R)):
+            wt_sh = _empty((C, R), td, weight.device)
         if dtype != L.F32 or need_t:
             ops.cast_weight(w2.detach(), R, C, None if gamma is None else gamma.detach(),
-                            None if dtype == L.F32 else w_sh, wt_sh, dtype)
+                            None if dtype == L.F32 else w_sh, wt_sh if need_t else None, dtype)
         self._cache[key] = (stamp, w_sh, wt_sh)
         return w_sh, wt_sh
+
+
+def _dst(sinks, i, shape, dev):
+    """Destination of parameter-gradient i: its slot in the flat gradient sink, or a fresh zero-filled tensor."""
+    if sinks is not None and sinks[i] is not None:
+        return sinks[i], True
+    return _zeros(shape, dev), False
 
 
 # ---------------------------------------------------------------------------------------------
@@ -148,7 +185,7 @@ class _Shadows:
 # ---------------------------------------------------------------------------------------------
 class _EmbedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, pe_w, pe_b, pos_k, pos_f, pos_t, cls, rt: _Ctx, sh: _Shadows):
+    def forward(ctx, x, pe_w, pe_b, pos_k, pos_f, pos_t, cls, rt: _Ctx, sh: _Shadows, sinks):
         cfg = rt.cfg
         B = x.shape[0]
         D, P, n = cfg.embed_dim, cfg.patch_dim, cfg.n_patches
@@ -168,6 +205,7 @@ class _EmbedFn(torch.autograd.Function):
         ops.cls_rows(cls, h, B, N, D, drop)
         ctx.rt, ctx.drop, ctx.grid3 = rt, drop, (Kp, Fp, Tp)
         ctx.pe_shape = pe_w.shape
+        ctx.sinks = sinks
         ctx.save_for_backward(cols)
         return h
 
@@ -175,6 +213,7 @@ class _EmbedFn(torch.autograd.Function):
     def backward(ctx, g0):
         (cols,) = ctx.saved_tensors
         rt, cfg = ctx.rt, ctx.rt.cfg
+        sk = ctx.sinks[0] if ctx.sinks is not None else None
         Kp, Fp, Tp = ctx.grid3
         g0 = g0.contiguous()
         B, N, D = g0.shape
@@ -183,74 +222,87 @@ class _EmbedFn(torch.autograd.Function):
         dev = g0.device
         gtok = _empty((B * n, D), td, dev)
         R = _empty((n, D), torch.float32, dev)
-        dcls = _empty((1, 1, D), torch.float32, dev)
-        ops.embed_bwd_prep(g0, B, n, D, ctx.drop, gtok, rt.dtype, R, dcls)
-        dpk = _empty((1, Kp, D), torch.float32, dev)
-        dpf = _empty((1, Fp, D), torch.float32, dev)
-        dpt = _empty((1, Tp, D), torch.float32, dev)
-        dpe_b = _empty((D,), torch.float32, dev)
-        ops.pos_grad_reduce(R, Kp, Fp, Tp, D, dpk, dpf, dpt, dpe_b)
-        dpe_w = _zeros((D, P), dev)
+        # parameter order of `sinks`: pe_w, pe_b, pos_k, pos_f, pos_t, cls
+        use = sk is not None
+        dcls = sk[5] if use else _empty((1, 1, D), torch.float32, dev)
+        ops.embed_bwd_prep(g0, B, n, D, ctx.drop, gtok, rt.dtype, R, dcls, accumulate=use)
+        dpk = sk[2] if use else _empty((1, Kp, D), torch.float32, dev)
+        dpf = sk[3] if use else _empty((1, Fp, D), torch.float32, dev)
+        dpt = sk[4] if use else _empty((1, Tp, D), torch.float32, dev)
+        dpe_b = sk[1] if use else _empty((D,), torch.float32, dev)
+        ops.pos_grad_reduce(R, Kp, Fp, Tp, D, dpk, dpf, dpt, dpe_b, accumulate=use)
+        dpe_w = sk[0] if use else _zeros((D, P), dev)
         ops.gemm(rt.engine, rt.dtype, gtok, cols, D, P, B * n, epilogue=L.EPI_ACCUM_F32, out=dpe_w,
                  trans_a=True, trans_b=True)
-        return None, dpe_w.reshape(ctx.pe_shape), dpe_b, dpk, dpf, dpt, dcls, None, None
+        if use:
+            rt.sink.mark_ready(ctx.sinks[1])
+            return (None,) * 10
+        return None, dpe_w.reshape(ctx.pe_shape), dpe_b, dpk, dpf, dpt, dcls, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------
 # encoder block (model.py:151-178): x + dp(ls1(attn(ln1 x)));  x + dp(ls2(mlp(ln2 x)))
 # ---------------------------------------------------------------------------------------------
+def _block_forward(h, n1w, n1b, qkvw, qkvb, pw, pb, g1, n2w, n2b, f1w, f1b, f2w, f2b, g2, s1, s2,
+                   rt: _Ctx, sh: _Shadows, layer: int, need_grad: bool):
+    """All launches of one encoder block's forward.  Returns (h_out, saved intermediates, dropout specs)."""
+    cfg = rt.cfg
+    B, N, D = h.shape
+    M, H = B * N, cfg.n_heads
+    hd, hid = D // H, f1w.shape[0]
+    E, T = rt.engine, rt.dtype
+    td = ops.torch_dtype(T)
+    dev = h.device
+
+    qkv_w, qkv_wt = sh.get((layer, "qkv"), qkvw, None, T, need_grad)
+    proj_w, proj_wt = sh.get((layer, "proj"), pw, g1, T, need_grad)
+    fc1_w, fc1_wt = sh.get((layer, "fc1"), f1w, None, T, need_grad)
+    fc2_w, fc2_wt = sh.get((layer, "fc2"), f2w, g2, T, need_grad)
+
+    d_attn = rt.drop(_site(layer, 0), cfg.attention_dropout)
+    d_proj = rt.drop(_site(layer, 1), cfg.dropout)
+    d_fc1 = rt.drop(_site(layer, 2), cfg.dropout)
+    d_fc2 = rt.drop(_site(layer, 3), cfg.dropout)
+
+    y1 = _empty((M, D), td, dev)
+    mean1, rstd1 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
+    ops.ln_fwd(h, D, n1w, n1b, y1, T, mean1, rstd1, M, D)
+    qkv = _empty((M, 3 * D), td, dev)
+    ops.gemm(E, T, y1, qkv_w, M, 3 * D, D, epilogue=L.EPI_STORE, out=qkv, bias=qkvb)
+    ao = _empty((M, D), td, dev)
+    lse = _empty((B, H, N), torch.float32, dev)
+    ops.attn_fwd(rt.attn_engine, T, qkv, ao, lse, B, N, H, hd, d_attn)
+    h_mid = torch.empty_like(h)
+    ops.gemm(E, T, ao, proj_w, M, D, D, epilogue=L.EPI_RESIDUAL, out=h_mid, bias=pb, resid=h, gamma=g1,
+             row_scale=s1, rows_per_group=N, drop=d_proj)
+
+    y2 = _empty((M, D), td, dev)
+    mean2, rstd2 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
+    ops.ln_fwd(h_mid, D, n2w, n2b, y2, T, mean2, rstd2, M, D)
+    hpre = _empty((M, hid), td, dev)
+    act = _empty((M, hid), td, dev)
+    ops.gemm(E, T, y2, fc1_w, M, hid, D, epilogue=L.EPI_BIAS_GELU, out=act, aux=hpre, bias=f1b, drop=d_fc1)
+    h_out = torch.empty_like(h)
+    ops.gemm(E, T, act, fc2_w, M, D, hid, epilogue=L.EPI_RESIDUAL, out=h_out, bias=f2b, resid=h_mid, gamma=g2,
+             row_scale=s2, rows_per_group=N, drop=d_fc2)
+    saved = (h, y1, mean1, rstd1, qkv, ao, lse, h_mid, y2, mean2, rstd2, hpre, act,
+             n1w, qkvw, pw, pb, g1, n2w, f1w, f2w, f2b, g2, s1, s2, qkv_wt, proj_wt, fc1_wt, fc2_wt)
+    return h_out, saved, (d_attn, d_proj, d_fc1, d_fc2)
+
+
 class _BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, n1w, n1b, qkvw, qkvb, pw, pb, g1, n2w, n2b, f1w, f1b, f2w, f2b, g2, s1, s2,
-                rt: _Ctx, sh: _Shadows, layer: int):
-        cfg = rt.cfg
-        B, N, D = h.shape
-        M, H = B * N, cfg.n_heads
-        hd, hid = D // H, f1w.shape[0]
-        E, T = rt.engine, rt.dtype
-        td = ops.torch_dtype(T)
-        dev = h.device
+                rt: _Ctx, sh: _Shadows, layer: int, sinks):
         need_grad = any(ctx.needs_input_grad)
-
-        qkv_w, qkv_wt = sh.get((layer, "qkv"), qkvw, None, T, need_grad)
-        proj_w, proj_wt = sh.get((layer, "proj"), pw, g1, T, need_grad)
-        fc1_w, fc1_wt = sh.get((layer, "fc1"), f1w, None, T, need_grad)
-        fc2_w, fc2_wt = sh.get((layer, "fc2"), f2w, g2, T, need_grad)
-
-        d_attn = rt.drop(_site(layer, 0), cfg.attention_dropout)
-        d_proj = rt.drop(_site(layer, 1), cfg.dropout)
-        d_fc1 = rt.drop(_site(layer, 2), cfg.dropout)
-        d_fc2 = rt.drop(_site(layer, 3), cfg.dropout)
-
-        y1 = _empty((M, D), td, dev)
-        mean1, rstd1 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
-        ops.ln_fwd(h, D, n1w, n1b, y1, T, mean1, rstd1, M, D)
-        qkv = _empty((M, 3 * D), td, dev)
-        ops.gemm(E, T, y1, qkv_w, M, 3 * D, D, epilogue=L.EPI_STORE, out=qkv, bias=qkvb)
-        ao = _empty((M, D), td, dev)
-        lse = _empty((B, H, N), torch.float32, dev)
-        ops.attn_fwd(rt.attn_engine, T, qkv, ao, lse, B, N, H, hd, d_attn)
-        h_mid = torch.empty_like(h)
-        ops.gemm(E, T, ao, proj_w, M, D, D, epilogue=L.EPI_RESIDUAL, out=h_mid, bias=pb, resid=h, gamma=g1,
-                 row_scale=s1, rows_per_group=N, drop=d_proj)
-
-        y2 = _empty((M, D), td, dev)
-        mean2, rstd2 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
-        ops.ln_fwd(h_mid, D, n2w, n2b, y2, T, mean2, rstd2, M, D)
-        hpre = _empty((M, hid), td, dev)
-        act = _empty((M, hid), td, dev)
-        ops.gemm(E, T, y2, fc1_w, M, hid, D, epilogue=L.EPI_BIAS_GELU, out=act, aux=hpre, bias=f1b, drop=d_fc1)
-        h_out = torch.empty_like(h)
-        ops.gemm(E, T, act, fc2_w, M, D, hid, epilogue=L.EPI_RESIDUAL, out=h_out, bias=f2b, resid=h_mid, gamma=g2,
-                 row_scale=s2, rows_per_group=N, drop=d_fc2)
-
+        h_out, saved, drops = _block_forward(h, n1w, n1b, qkvw, qkvb, pw, pb, g1, n2w, n2b, f1w, f1b, f2w, f2b, g2,
+                                             s1, s2, rt, sh, layer, need_grad)
         if need_grad:
             ctx.rt, ctx.layer = rt, layer
-            ctx.drops = (d_attn, d_proj, d_fc1, d_fc2)
+            ctx.drops = drops
             ctx.has_ls = g1 is not None
-            ctx.save_for_backward(h, y1, mean1, rstd1, qkv, ao, lse, h_mid, y2, mean2, rstd2, hpre, act,
-                                  n1w, qkvw, pw, pb, g1, n2w, f1w, f2w, f2b, g2, s1, s2,
-                                  qkv_wt, proj_wt, fc1_wt, fc2_wt)
+            ctx.sinks = sinks
+            ctx.save_for_backward(*saved)
         return h_out
 
     @staticmethod
@@ -259,6 +311,7 @@ class _BlockFn(torch.autograd.Function):
          n1w, qkvw, pw, pb, g1, n2w, f1w, f2w, f2b, g2, s1, s2,
          qkv_wt, proj_wt, fc1_wt, fc2_wt) = ctx.saved_tensors
         rt, cfg = ctx.rt, ctx.rt.cfg
+        sk = ctx.sinks[0] if ctx.sinks is not None else None
         d_attn, d_proj, d_fc1, d_fc2 = ctx.drops
         E, T = rt.engine, rt.dtype
         td = ops.torch_dtype(T)
@@ -268,31 +321,47 @@ class _BlockFn(torch.autograd.Function):
         hd, hid = D // H, f1w.shape[0]
         dev = g_out.device
         f32 = torch.float32
+        # index of each parameter in the sink-view tuple
+        (I_N1W, I_N1B, I_QKVW, I_QKVB, I_PW, I_PB, I_G1, I_N2W, I_N2B, I_F1W, I_F1B, I_F2W, I_F2B, I_G2) = range(14)
+        use = sk is not None
 
         # ---- MLP branch -------------------------------------------------------------------
         gp2 = _empty((M, D), td, dev)
-        cs2 = _zeros((D,), dev)
+        if ctx.has_ls:
+            cs2 = _zeros((D,), dev)
+        else:
+            cs2, _ = _dst(sk, I_F2B, (D,), dev)            # without LayerScale colsum(gp) IS the bias gradient
         ops.branch_grad_prep(g_out, M, D, s2, N, d_fc2, gp2, T, cs2)
         dh = _empty((M, hid), td, dev)   # grad wrt fc1 pre-activation
         ops.gemm(E, T, gp2, fc2_wt, M, hid, D, epilogue=L.EPI_GELU_BWD, out=dh, aux=hpre, drop=d_fc1)
-        G2 = _zeros((D, hid), dev)
+        if ctx.has_ls:
+            G2 = _zeros((D, hid), dev)
+        else:
+            G2, _ = _dst(sk, I_F2W, (D, hid), dev)
         ops.gemm(E, T, gp2, act, D, hid, M, epilogue=L.EPI_ACCUM_F32, out=G2, trans_a=True, trans_b=True)
         if ctx.has_ls:
-            d_f2w, d_g2, d_f2b = torch.empty_like(f2w), _empty((D,), f32, dev), _empty((D,), f32, dev)
-            ops.ls_finalize(G2, f2w, g2, f2b, cs2, d_f2w, d_g2, d_f2b, D, hid)
+            if use:
+                d_f2w, d_g2, d_f2b = sk[I_F2W], sk[I_G2], sk[I_F2B]
+            else:
+                d_f2w, d_g2, d_f2b = torch.empty_like(f2w), _empty((D,), f32, dev), _empty((D,), f32, dev)
+            ops.ls_finalize(G2, f2w, g2, f2b, cs2, d_f2w, d_g2, d_f2b, D, hid, accumulate=use)
         else:
             d_f2w, d_g2, d_f2b = G2, None, cs2
-        d_f1b = _zeros((hid,), dev)
+        d_f1b, _ = _dst(sk, I_F1B, (hid,), dev)
         ops.colsum(dh, T, M, hid, hid, d_f1b)
-        d_f1w = _zeros((hid, D), dev)
+        d_f1w, _ = _dst(sk, I_F1W, (hid, D), dev)
         ops.gemm(E, T, dh, y2, hid, D, M, epilogue=L.EPI_ACCUM_F32, out=d_f1w, trans_a=True, trans_b=True)
         dy2 = _empty((M, D), td, dev)
         ops.gemm(E, T, dh, fc1_wt, M, D, hid, epilogue=L.EPI_STORE, out=dy2)
         del dh
         g_mid = torch.empty_like(g_out)
-        d_n2w, d_n2b = _zeros((D,), dev), _zeros((D,), dev)
+        d_n2w, _ = _dst(sk, I_N2W, (D,), dev)
+        d_n2b, _ = _dst(sk, I_N2B, (D,), dev)
         gp1 = _empty((M, D), td, dev)
-        cs1 = _zeros((D,), dev)
+        if ctx.has_ls:
+            cs1 = _zeros((D,), dev)
+        else:
+            cs1, _ = _dst(sk, I_PB, (D,), dev)
         ops.ln_bwd(dy2, T, h_mid, D, mean2, rstd2, n2w, g_out, g_mid, D, d_n2w, d_n2b, M, D,
                    gp=gp1, row_scale=s1, rows_per_group=N, drop=d_proj, gp_colsum=cs1)
         del dy2
@@ -300,28 +369,38 @@ class _BlockFn(torch.autograd.Function):
         # ---- attention branch ---------------------------------------------------------------
         dao = _empty((M, D), td, dev)
         ops.gemm(E, T, gp1, proj_wt, M, D, D, epilogue=L.EPI_STORE, out=dao)
-        Gp = _zeros((D, D), dev)
+        if ctx.has_ls:
+            Gp = _zeros((D, D), dev)
+        else:
+            Gp, _ = _dst(sk, I_PW, (D, D), dev)
         ops.gemm(E, T, gp1, ao, D, D, M, epilogue=L.EPI_ACCUM_F32, out=Gp, trans_a=True, trans_b=True)
         if ctx.has_ls:
-            d_pw, d_g1, d_pb = torch.empty_like(pw), _empty((D,), f32, dev), _empty((D,), f32, dev)
-            ops.ls_finalize(Gp, pw, g1, pb, cs1, d_pw, d_g1, d_pb, D, D)
+            if use:
+                d_pw, d_g1, d_pb = sk[I_PW], sk[I_G1], sk[I_PB]
+            else:
+                d_pw, d_g1, d_pb = torch.empty_like(pw), _empty((D,), f32, dev), _empty((D,), f32, dev)
+            ops.ls_finalize(Gp, pw, g1, pb, cs1, d_pw, d_g1, d_pb, D, D, accumulate=use)
         else:
             d_pw, d_g1, d_pb = Gp, None, cs1
         dqkv = _empty((M, 3 * D), td, dev)
         ops.attn_bwd(rt.attn_engine, T, qkv, ao, dao, lse, dqkv, B, N, H, hd, d_attn)
-        d_qkvb = _zeros((3 * D,), dev)
+        d_qkvb, _ = _dst(sk, I_QKVB, (3 * D,), dev)
         ops.colsum(dqkv, T, M, 3 * D, 3 * D, d_qkvb)
-        d_qkvw = _zeros((3 * D, D), dev)
+        d_qkvw, _ = _dst(sk, I_QKVW, (3 * D, D), dev)
         ops.gemm(E, T, dqkv, y1, 3 * D, D, M, epilogue=L.EPI_ACCUM_F32, out=d_qkvw, trans_a=True, trans_b=True)
         dy1 = _empty((M, D), td, dev)
         ops.gemm(E, T, dqkv, qkv_wt, M, D, 3 * D, epilogue=L.EPI_STORE, out=dy1)
         del dqkv
         g_in = torch.empty_like(g_out)
-        d_n1w, d_n1b = _zeros((D,), dev), _zeros((D,), dev)
+        d_n1w, _ = _dst(sk, I_N1W, (D,), dev)
+        d_n1b, _ = _dst(sk, I_N1B, (D,), dev)
         ops.ln_bwd(dy1, T, h, D, mean1, rstd1, n1w, g_mid, g_in, D, d_n1w, d_n1b, M, D)
 
+        if use:
+            rt.sink.mark_ready(ctx.sinks[1])
+            return (g_in,) + (None,) * 20
         return (g_in, d_n1w, d_n1b, d_qkvw, d_qkvb, d_pw, d_pb, d_g1, d_n2w, d_n2b, d_f1w, d_f1b, d_f2w, d_f2b,
-                d_g2, None, None, None, None, None)
+                d_g2, None, None, None, None, None, None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -329,7 +408,7 @@ class _BlockFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 class _HeadFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, nw, nb, w0, b0, w3, b3, rt: _Ctx):
+    def forward(ctx, h, nw, nb, w0, b0, w3, b3, rt: _Ctx, sinks):
         cfg = rt.cfg
         B, N, D = h.shape
         C = w3.shape[0]
@@ -344,36 +423,42 @@ class _HeadFn(torch.autograd.Function):
         ops.gemm(E, T, c, w0.detach(), B, D, D, epilogue=L.EPI_BIAS_GELU, out=z, aux=zpre, bias=b0, drop=drop)
         logits = _empty((B, C), f32, dev)
         ops.gemm(E, T, z, w3.detach(), B, C, D, epilogue=L.EPI_STORE, out=logits, bias=b3)
-        ctx.drop, ctx.N = drop, N
+        ctx.drop, ctx.N, ctx.rt, ctx.sinks = drop, N, rt, sinks
         ctx.save_for_backward(h, c, mean, rstd, zpre, z, nw, w0, w3)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         h, c, mean, rstd, zpre, z, nw, w0, w3 = ctx.saved_tensors
+        sk = ctx.sinks[0] if ctx.sinks is not None else None
         B, N, D = h.shape
         C = w3.shape[0]
         dev = h.device
         f32 = torch.float32
         E, T = L.ENGINE_SIMT, L.F32
         dlogits = dlogits.contiguous().to(f32)
-        d_w3 = _zeros((C, D), dev)
+        # parameter order of `sinks`: nw, nb, w0, b0, w3, b3
+        d_w3, _ = _dst(sk, 4, (C, D), dev)
         ops.gemm(E, T, dlogits, z, C, D, B, epilogue=L.EPI_ACCUM_F32, out=d_w3, trans_a=True, trans_b=True)
-        d_b3 = _zeros((C,), dev)
+        d_b3, _ = _dst(sk, 5, (C,), dev)
         ops.colsum(dlogits, T, B, C, C, d_b3)
         dzpre = _empty((B, D), f32, dev)   # (dlogits @ w3) * drop * gelu'(zpre)
         ops.gemm(E, T, dlogits, w3.detach(), B, D, C, epilogue=L.EPI_GELU_BWD, out=dzpre, aux=zpre, trans_b=True,
                  drop=ctx.drop)
-        d_w0 = _zeros((D, D), dev)
+        d_w0, _ = _dst(sk, 2, (D, D), dev)
         ops.gemm(E, T, dzpre, c, D, D, B, epilogue=L.EPI_ACCUM_F32, out=d_w0, trans_a=True, trans_b=True)
-        d_b0 = _zeros((D,), dev)
+        d_b0, _ = _dst(sk, 3, (D,), dev)
         ops.colsum(dzpre, T, B, D, D, d_b0)
         dc = _empty((B, D), f32, dev)
         ops.gemm(E, T, dzpre, w0.detach(), B, D, D, epilogue=L.EPI_STORE, out=dc, trans_b=True)
         g = _zeros((B, N, D), dev)         # only the CLS rows receive gradient
-        d_nw, d_nb = _zeros((D,), dev), _zeros((D,), dev)
+        d_nw, _ = _dst(sk, 0, (D,), dev)
+        d_nb, _ = _dst(sk, 1, (D,), dev)
         ops.ln_bwd(dc, T, h, N * D, mean, rstd, nw, None, g, N * D, d_nw, d_nb, B, D)
-        return g, d_nw, d_nb, d_w0, d_b0, d_w3, d_b3, None
+        if sk is not None:
+            ctx.rt.sink.mark_ready(ctx.sinks[1])
+            return (g,) + (None,) * 8
+        return g, d_nw, d_nb, d_w0, d_b0, d_w3, d_b3, None, None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -409,6 +494,14 @@ class _BlockParams(nn.Module):
         self.mlp = _MlpParams(dim, hidden)
         self.ls2 = _Gamma(dim, layer_scale_init) if layer_scale_init > 0 else nn.Identity()
         self.drop_path_rate = float(drop_path)
+
+    def tensors(self):
+        """Parameters in the argument order of _BlockFn (None where LayerScale is disabled)."""
+        g1 = self.ls1.gamma if isinstance(self.ls1, _Gamma) else None
+        g2 = self.ls2.gamma if isinstance(self.ls2, _Gamma) else None
+        return (self.norm1.weight, self.norm1.bias, self.attn.qkv.weight, self.attn.qkv.bias,
+                self.attn.proj.weight, self.attn.proj.bias, g1, self.norm2.weight, self.norm2.bias,
+                self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, g2)
 
 
 class Temporal3DViT(nn.Module):
@@ -450,6 +543,10 @@ class Temporal3DViT(nn.Module):
                                   nn.Linear(D, config.n_classes))
         self._reset_parameters()
         self._shadows = _Shadows()
+        self._grad_sink: Optional[GradSink] = None
+        # what the last train-mode forward drew: {"seed": int, "drop_path": [(s1, s2) per block]} -- lets the parity
+        # tests rebuild every dropout / DropPath mask with oracle/dropout_ref.py
+        self.last_draws: Optional[dict] = None
 
     # same initialisation recipe and RNG consumption order as the reference (model.py:257-274)
     def _reset_parameters(self) -> None:
@@ -463,6 +560,30 @@ class Temporal3DViT(nn.Module):
             elif isinstance(m, nn.LayerNorm):
                 nn.init.ones_(m.weight)
                 nn.init.zeros_(m.bias)
+
+    # ------------------------------------------------------------------------------------------
+    # hooks for the optimizer / data-parallel layers of this package
+    # ------------------------------------------------------------------------------------------
+    def invalidate_shadows(self) -> None:
+        """Force the bf16 operand copies of the weights to be rebuilt at the next forward.  Needed only after the
+        parameters were modified by something that neither bumps their autograd version counter nor is part of this
+        package (the fused optimizer and the DDP broadcast do it themselves)."""
+        self._shadows.invalidate()
+
+    def attach_grad_sink(self, sink: Optional[GradSink] = None, bucket_mb: float = 32.0) -> GradSink:
+        """Make the backward kernels accumulate parameter gradients straight into flat buckets (gradsink.py)."""
+        if self._grad_sink is None:
+            self._grad_sink = sink if sink is not None else GradSink(list(self.parameters()), bucket_mb)
+        return self._grad_sink
+
+    def detach_grad_sink(self) -> None:
+        self._grad_sink = None
+
+    def _apply(self, fn, *args, **kwargs):
+        if self._grad_sink is not None:
+            raise RuntimeError("move / cast the model before creating FusedAdamW or BucketedAllReduce: its parameters "
+                               "and gradients live in flat buffers now")
+        return super()._apply(fn, *args, **kwargs)
 
     # ------------------------------------------------------------------------------------------
     def _runtime(self, x: torch.Tensor) -> _Ctx:
@@ -483,10 +604,13 @@ class Temporal3DViT(nn.Module):
         if cfg.embed_dim % 4 != 0:
             raise ValueError("embed_dim must be a multiple of 4")
         seed = 0
-        if self.training:
+        if self.training and (cfg.dropout > 0.0 or cfg.attention_dropout > 0.0):
             hi, lo = torch.randint(0, 2 ** 31 - 1, (2,)).tolist()   # CPU generator: honours torch.manual_seed
             seed = (hi << 31) | lo
-        return _Ctx(engine, attn_engine, dtype, self.training, seed, cfg)
+        sink = self._grad_sink if (self.training and torch.is_grad_enabled()) else None
+        if sink is not None:
+            sink.begin_pass()
+        return _Ctx(engine, attn_engine, dtype, self.training, seed, cfg, sink)
 
     def _check_input(self, x: torch.Tensor) -> torch.Tensor:
         cfg = self.config
@@ -499,61 +623,85 @@ class Temporal3DViT(nn.Module):
                              f"dim of 1, got {tuple(x.shape)}")
         return x.to(torch.float32).contiguous()
 
-    def _drop_path_scale(self, rate: float, B: int, device) -> Optional[torch.Tensor]:
-        """Per-sample DropPath multiplier floor(keep + U[0,1)) / keep (model.py:64-71)."""
-        if rate == 0.0 or not self.training:
+    def _drop_path_scales(self, B: int, device):
+        """Per-sample DropPath multipliers floor(keep + U[0,1)) / keep (model.py:64-71) for both branches of every
+        block, drawn with ONE torch.rand per forward; entries are None where the rate is 0 / in eval mode."""
+        Lyr = self.config.n_layers
+        rates = [blk.drop_path_rate for blk in self.blocks]
+        if not self.training or not any(r > 0.0 for r in rates):
+            return [(None, None)] * Lyr
+        keep = getattr(self, "_dp_keep", None)
+        if keep is None or keep.device != device:
+            keep = torch.tensor([1.0 - r for r in rates for _ in (0, 1)], dtype=torch.float32, device=device)[:, None]
+            self._dp_keep = keep
+        scales = torch.floor(keep + torch.rand(2 * Lyr, B, device=device, dtype=torch.float32)) / keep
+        return [(scales[2 * i], scales[2 * i + 1]) if rates[i] > 0.0 else (None, None) for i in range(Lyr)]
+
+    def _sinks_for(self, rt: _Ctx, params):
+        """(gradient-sink views, the Parameter objects themselves) in the Function's argument order, or None."""
+        if rt.sink is None:
             return None
-        keep = 1.0 - rate
-        return torch.floor(keep + torch.rand(B, device=device, dtype=torch.float32)) / keep
+        return tuple(None if p is None else rt.sink.view(p) for p in params), tuple(p for p in params if p is not None)
 
     def _embed(self, x: torch.Tensor, rt: _Ctx) -> torch.Tensor:
-        return _EmbedFn.apply(x, self.patch_embed.weight, self.patch_embed.bias, self.pos_embed_k, self.pos_embed_f,
-                              self.pos_embed_t, self.cls_token, rt, self._shadows)
+        params = (self.patch_embed.weight, self.patch_embed.bias, self.pos_embed_k, self.pos_embed_f,
+                  self.pos_embed_t, self.cls_token)
+        return _EmbedFn.apply(x, *params, rt, self._shadows, self._sinks_for(rt, params))
 
-    def _block(self, i: int, h: torch.Tensor, rt: _Ctx) -> torch.Tensor:
-        blk = self.blocks[i]
-        B = h.shape[0]
-        g1 = blk.ls1.gamma if isinstance(blk.ls1, _Gamma) else None
-        g2 = blk.ls2.gamma if isinstance(blk.ls2, _Gamma) else None
-        s1 = self._drop_path_scale(blk.drop_path_rate, B, h.device)
-        s2 = self._drop_path_scale(blk.drop_path_rate, B, h.device)
-        return _BlockFn.apply(h, blk.norm1.weight, blk.norm1.bias, blk.attn.qkv.weight, blk.attn.qkv.bias,
-                              blk.attn.proj.weight, blk.attn.proj.bias, g1, blk.norm2.weight, blk.norm2.bias,
-                              blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias, g2,
-                              s1, s2, rt, self._shadows, i)
+    def _block(self, i: int, h: torch.Tensor, rt: _Ctx, dp) -> torch.Tensor:
+        params = self.blocks[i].tensors()
+        return _BlockFn.apply(h, *params, dp[0], dp[1], rt, self._shadows, i, self._sinks_for(rt, params))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x: (B, K, F, T) or (B, 1, K, F, T) fp32 on a B200 -> logits (B, n_classes) fp32."""
-        with torch.autocast(device_type="cuda", enabled=False):
+        if not x.is_cuda:
+            self._runtime(x)   # raises: no CPU fallback
+        with torch.cuda.device(x.device), torch.autocast(device_type="cuda", enabled=False):
             rt = self._runtime(x)
             x = self._check_input(x)
+            dps = self._drop_path_scales(x.shape[0], x.device)
+            if self.training:
+                self.last_draws = {"seed": rt.seed, "drop_path": dps}
             h = self._embed(x, rt)
             for i in range(self.config.n_layers):
-                h = self._block(i, h, rt)
-            return _HeadFn.apply(h, self.norm.weight, self.norm.bias, self.head[0].weight, self.head[0].bias,
-                                 self.head[3].weight, self.head[3].bias, rt)
+                h = self._block(i, h, rt, dps[i])
+            params = (self.norm.weight, self.norm.bias, self.head[0].weight, self.head[0].bias,
+                      self.head[3].weight, self.head[3].bias)
+            return _HeadFn.apply(h, *params, rt, self._sinks_for(rt, params))
 
     def get_attention_maps(self, x: torch.Tensor) -> List[torch.Tensor]:
-        """Per-block softmax(q k^T / sqrt(hd)) of shape (B, H, N, N), as the reference (model.py:325-350)."""
+        """Per-block softmax(q k^T / sqrt(hd)) of shape (B, H, N, N), as the reference (model.py:325-350).
+
+        Tensor-core path: each block runs its normal forward launches (qkv GEMM, flash attention -> row
+        log-sum-exp), then the probabilities are materialised tile by tile by the tcgen05 GEMM with the
+        SOFTMAX_PROBS epilogue, P = exp(scale * Q K^T - lse), one launch per (sample, head).  The fp32
+        verification precision uses the CUDA-core row-softmax kernel."""
+        if not x.is_cuda:
+            self._runtime(x)
         maps: List[torch.Tensor] = []
-        with torch.autocast(device_type="cuda", enabled=False):
+        with torch.cuda.device(x.device), torch.autocast(device_type="cuda", enabled=False), torch.no_grad():
             rt = self._runtime(x)
             x = self._check_input(x)
             cfg = self.config
             D, H = cfg.embed_dim, cfg.n_heads
-            td = ops.torch_dtype(rt.dtype)
+            hd = D // H
+            dps = self._drop_path_scales(x.shape[0], x.device)
             h = self._embed(x, rt)
             B, N, _ = h.shape
             for i, blk in enumerate(self.blocks):
-                with torch.no_grad():
-                    y = torch.empty((B * N, D), dtype=td, device=h.device)
-                    ops.ln_fwd(h.detach(), D, blk.norm1.weight, blk.norm1.bias, y, rt.dtype, None, None, B * N, D)
-                    w_sh, _ = self._shadows.get((i, "qkv"), blk.attn.qkv.weight, None, rt.dtype, False)
-                    qkv = torch.empty((B * N, 3 * D), dtype=td, device=h.device)
-                    ops.gemm(rt.engine, rt.dtype, y, w_sh, B * N, 3 * D, D, epilogue=L.EPI_STORE, out=qkv,
-                             bias=blk.attn.qkv.bias)
-                    probs = torch.empty((B, H, N, N), dtype=torch.float32, device=h.device)
-                    ops.attn_probs(rt.dtype, qkv, probs, B, N, H, D // H)
-                    maps.append(probs)
-                h = self._block(i, h, rt)
+                h_out, saved, _ = _block_forward(h, *blk.tensors(), dps[i][0], dps[i][1], rt, self._shadows, i, False)
+                qkv, lse = saved[4], saved[6]
+                probs = torch.empty((B, H, N, N), dtype=torch.float32, device=h.device)
+                if rt.attn_engine == L.ENGINE_TCGEN05:
+                    lse_flat = lse.reshape(-1)
+                    for b in range(B):
+                        for hh in range(H):
+                            ops.gemm(rt.engine, rt.dtype, qkv, qkv, N, N, hd, epilogue=L.EPI_SOFTMAX_PROBS, out=probs,
+                                     lda=3 * D, ldb=3 * D, ldo=N, row_scale=lse_flat, alpha=hd ** -0.5,
+                                     a_offset=b * N * 3 * D + hh * hd, b_offset=b * N * 3 * D + D + hh * hd,
+                                     out_offset=(b * H + hh) * N * N, row_scale_offset=(b * H + hh) * N)
+                else:
+                    ops.attn_probs(rt.dtype, qkv, probs, B, N, H, hd)
+                maps.append(probs)
+                h = h_out
         return maps

@@ -23,7 +23,8 @@ LAUNCHES = {"count": 0}
 TIMED = None
 _KERNELS_PER_CALL = {"gemm": 1, "attn_fwd": 1, "attn_bwd": 3, "attn_bwd_simt": 2, "attn_probs": 1, "im2col": 1,
                      "ln_fwd": 1, "ln_bwd": 1, "branch_grad_prep": 1, "colsum": 1, "cast_weight": 1,
-                     "ls_finalize": 1, "cls_rows": 1, "embed_bwd_prep": 1, "pos_grad_reduce": 1, "adamw": 1}
+                     "ls_finalize": 1, "cls_rows": 1, "embed_bwd_prep": 1, "pos_grad_reduce": 1, "adamw": 1,
+                     "shadow_t_multi": 1, "ce_loss": 1}
 
 
 def _count(name: str) -> None:
@@ -89,7 +90,9 @@ def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
 def gemm(engine: int, dtype: int, a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, epilogue: int,
          out: torch.Tensor, lda: Optional[int] = None, ldb: Optional[int] = None, ldo: Optional[int] = None,
          trans_a: bool = False, trans_b: bool = False, bias=None, aux=None, resid=None, gamma=None, row_scale=None,
-         rows_per_group: int = 0, drop: DropSpec = None, pos=None, grid3=None, split_k: int = 0) -> None:
+         rows_per_group: int = 0, drop: DropSpec = None, pos=None, grid3=None, split_k: int = 0,
+         alpha: float = 1.0, a_offset: int = 0, b_offset: int = 0, out_offset: int = 0,
+         row_scale_offset: int = 0) -> None:
     """C[M,N] = op(A) op(B)^T with a fused epilogue (see tvit_gemm in include/tvit.h)."""
     td = torch_dtype(dtype)
     _req(a, td, "gemm A")
@@ -98,21 +101,23 @@ def gemm(engine: int, dtype: int, a: torch.Tensor, b: torch.Tensor, M: int, N: i
     args.engine, args.dtype = engine, dtype
     args.trans_a, args.trans_b = int(trans_a), int(trans_b)
     args.M, args.N, args.K = M, N, K
-    args.A, args.lda = a.data_ptr(), (lda if lda is not None else (M if trans_a else K))
-    args.B, args.ldb = b.data_ptr(), (ldb if ldb is not None else (N if trans_b else K))
+    # *_offset: element offsets into the operand tensors (sub-matrix views, e.g. one head of the packed qkv)
+    args.A, args.lda = a.data_ptr() + a_offset * a.element_size(), (lda if lda is not None else (M if trans_a else K))
+    args.B, args.ldb = b.data_ptr() + b_offset * b.element_size(), (ldb if ldb is not None else (N if trans_b else K))
     args.epilogue = epilogue
-    args.out, args.ldo = out.data_ptr(), (ldo if ldo is not None else N)
+    args.out, args.ldo = out.data_ptr() + out_offset * out.element_size(), (ldo if ldo is not None else N)
     args.bias = _ptr(bias)
     args.aux, args.ldaux = _ptr(aux), N
     args.resid, args.ldres = _ptr(resid), N
     args.gamma = _ptr(gamma)
-    args.row_scale = _ptr(row_scale)
+    args.row_scale = None if row_scale is None else row_scale.data_ptr() + 4 * row_scale_offset
     args.rows_per_group = rows_per_group
     args.drop = _drop(drop)
     if pos is not None:
         args.pos_k, args.pos_f, args.pos_t = (p.data_ptr() for p in pos)
         args.Kp, args.Fp, args.Tp = grid3
     args.split_k = split_k
+    args.alpha = alpha
     _count("gemm")
     with _timed(("gemm_e%d%s" % (epilogue, "_tn" if trans_a else "")) if TIMED is None or "detail" not in TIMED
                 else "gemm_e%d%s_N%d_K%d" % (epilogue, "_tn" if trans_a else "", N, K)):
@@ -126,10 +131,24 @@ def attn_fwd(engine, dtype, qkv, out, lse, B, N, H, hd, drop: DropSpec = None) -
                                        _drop_ptr(drop), _stream()), "tvit_attn_fwd")
 
 
+# grow-only scratch buffers, one per (device, stream): every use is stream-ordered on the stream it is keyed by, so
+# consecutive backward launches reuse the same block without a trip through the allocator
+_WORKSPACES = {}
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (device.index, _stream())
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, B, N, H, hd, drop: DropSpec = None) -> None:
     lib = L.load()
     nbytes = int(lib.tvit_attn_bwd_workspace_bytes(engine, dtype, B, N, H, hd))
-    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qkv.device)
+    ws = workspace(nbytes, qkv.device)
     _count("attn_bwd" if engine == L.ENGINE_TCGEN05 else "attn_bwd_simt")
     with _timed("attn_bwd"):
         L.check(lib.tvit_attn_bwd(engine, dtype, qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
@@ -182,10 +201,10 @@ def cast_weight(w, R, C, row_scale, out, out_t, dtype) -> None:
             "tvit_cast_weight")
 
 
-def ls_finalize(G, W, gamma, bias, cs, dW, dgamma, dbias, R, C) -> None:
+def ls_finalize(G, W, gamma, bias, cs, dW, dgamma, dbias, R, C, accumulate: bool = False) -> None:
     _count("ls_finalize")
     L.check(L.load().tvit_ls_finalize(G.data_ptr(), _ptr(W), _ptr(gamma), _ptr(bias), cs.data_ptr(), dW.data_ptr(),
-                                      _ptr(dgamma), _ptr(dbias), R, C, _stream()), "tvit_ls_finalize")
+                                      _ptr(dgamma), _ptr(dbias), R, C, int(accumulate), _stream()), "tvit_ls_finalize")
 
 
 def cls_rows(cls, h, B, N, D, drop: DropSpec) -> None:
@@ -194,19 +213,45 @@ def cls_rows(cls, h, B, N, D, drop: DropSpec) -> None:
             "tvit_cls_rows")
 
 
-def embed_bwd_prep(g0, B, n, D, drop: DropSpec, gtok, dtype, R, dcls) -> None:
+def embed_bwd_prep(g0, B, n, D, drop: DropSpec, gtok, dtype, R, dcls, accumulate: bool = False) -> None:
     _count("embed_bwd_prep")
     L.check(L.load().tvit_embed_bwd_prep(g0.data_ptr(), B, n, D, _drop_ptr(drop), gtok.data_ptr(), dtype,
-                                         R.data_ptr(), dcls.data_ptr(), _stream()), "tvit_embed_bwd_prep")
+                                         R.data_ptr(), dcls.data_ptr(), int(accumulate), _stream()),
+            "tvit_embed_bwd_prep")
 
 
-def pos_grad_reduce(R, Kp, Fp, Tp, D, dpk, dpf, dpt, dbias) -> None:
+def pos_grad_reduce(R, Kp, Fp, Tp, D, dpk, dpf, dpt, dbias, accumulate: bool = False) -> None:
     _count("pos_grad_reduce")
     L.check(L.load().tvit_pos_grad_reduce(R.data_ptr(), Kp, Fp, Tp, D, dpk.data_ptr(), dpf.data_ptr(),
-                                          dpt.data_ptr(), dbias.data_ptr(), _stream()), "tvit_pos_grad_reduce")
+                                          dpt.data_ptr(), dbias.data_ptr(), int(accumulate), _stream()),
+            "tvit_pos_grad_reduce")
 
 
-def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> None:
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, shadow=None) -> None:
+    """Fused AdamW over flat fp32 tensors (p is updated through its raw pointer: the autograd version counter is
+    bumped here so that every cache keyed on ``_version`` -- the operand shadows -- sees the change)."""
+    _req(p, torch.float32, "adamw p")
+    _req(g, torch.float32, "adamw g")
+    if shadow is not None:
+        _req(shadow, torch.bfloat16, "adamw shadow")
     _count("adamw")
-    L.check(L.load().tvit_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
-                                eps, weight_decay, step, grad_scale, _stream()), "tvit_adamw")
+    L.check(L.load().tvit_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), p.numel(), lr,
+                                beta1, beta2, eps, weight_decay, step, grad_scale, _stream()), "tvit_adamw")
+    torch.autograd.graph.increment_version(p)
+
+
+def shadow_t_multi(descs_device: torch.Tensor, count: int, total_tiles: int, dtype: int) -> None:
+    _count("shadow_t_multi")
+    L.check(L.load().tvit_shadow_t_multi(descs_device.data_ptr(), count, total_tiles, dtype, _stream()),
+            "tvit_shadow_t_multi")
+
+
+def ce_loss(logits, labels, class_weight, label_smoothing, loss, dlogits, metric_acc=None, prob_out=None,
+            label_out=None) -> None:
+    _req(logits, torch.float32, "ce_loss logits")
+    _req(labels, torch.int64, "ce_loss labels")
+    B, C = logits.shape
+    _count("ce_loss")
+    L.check(L.load().tvit_ce_loss(logits.data_ptr(), labels.data_ptr(), _ptr(class_weight), float(label_smoothing), B,
+                                  C, _ptr(loss), _ptr(dlogits), _ptr(metric_acc), _ptr(prob_out), _ptr(label_out),
+                                  _stream()), "tvit_ce_loss")

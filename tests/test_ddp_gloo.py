@@ -46,7 +46,26 @@ def _worker(rank, world, port, q):
             loss.backward()
             ddp.finish()
         grads = [p.grad.clone() for p in net.parameters()]
-        q.put((rank, len(ddp.buckets), ddp.launched, [g.numpy() for g in grads]))
+        launched = ddp.launched
+        # gradient accumulation: two half-batches, the first under no_sync(), must give the same averaged gradient
+        net.zero_grad(set_to_none=True)
+        h = xs.shape[0] // 2
+        with ddp.no_sync():
+            (0.5 * torch.nn.functional.cross_entropy(net(xs[:h]), ys[:h])).backward()
+            ddp.finish()                   # no-op inside no_sync
+        (0.5 * torch.nn.functional.cross_entropy(net(xs[h:]), ys[h:])).backward()
+        ddp.finish()
+        acc = [p.grad.clone().numpy() for p in net.parameters()]
+        # a second backward without no_sync() while buckets are in flight must raise, not corrupt the buckets
+        net.zero_grad(set_to_none=True)
+        torch.nn.functional.cross_entropy(net(xs), ys).backward()
+        raised = False
+        try:
+            torch.nn.functional.cross_entropy(net(xs), ys).backward()
+        except RuntimeError as e:
+            raised = "no_sync" in str(e)
+        ddp.finish()
+        q.put((rank, len(ddp.buckets), launched, [g.numpy() for g in grads], acc, raised))
     finally:
         dist.destroy_process_group()
 
@@ -69,10 +88,12 @@ def test_bucketed_allreduce_world2_matches_single_process():
     # mean over ranks of per-rank mean losses == mean over the full batch (equal shard sizes)
     torch.nn.functional.cross_entropy(net(x), y).backward()
     ref = [p.grad for p in net.parameters()]
-    for rank, nb, launched, grads in results:
+    for rank, nb, launched, grads, acc, raised in results:
         assert nb >= 3 and launched == 2 * nb
-        for a, b in zip(grads, ref):
+        assert raised, "double backward without no_sync() must raise"
+        for a, b, c in zip(grads, ref, acc):
             assert torch.allclose(torch.from_numpy(a), b, atol=1e-6), rank
+            assert torch.allclose(torch.from_numpy(c), b, atol=1e-6), rank
 
 
 def test_requires_initialised_process_group():

@@ -1,8 +1,14 @@
-"""Shapes of the other BASELINE.json configs at reduced depth/batch (B200 only): the large variant
-(D768/H12), the long-sequence variant (32x128x512 -> N = 16385 tokens) and the full configs[1] token count
-(N = 2049).  The bf16 tensor-core path is compared with the on-device fp32 verification path (itself pinned to
-the reference by the golden-vector and fp64-oracle tests), because the fp64 oracle's O(N^2) score tensors do
-not fit these sizes comfortably."""
+"""Shapes of the BASELINE.json configs at reduced depth/batch (B200 only).
+
+* Directly against the fp64 oracle (the restatement pinned to the real reference): the full configs[1] token count
+  (8x128x256 -> N = 2049, D384/H6), the large variant's width at that token count (D768/H12, N = 2049) and the
+  real-data shape 8x64x488 -> N = 1953.  The oracle's (B,H,N,N) fp64 score tensors are 0.2-0.4 GB
+  each at batch 1 and fit a B200 easily.
+* The long-sequence variant (32x128x512 -> N = 16385) would need 13 GB per fp64 score tensor and several of them
+  alive for backward; there the bf16 tensor-core path is compared with the on-device fp32 verification path, which the
+  golden-vector, fp64-oracle and train-mode tests pin to the reference.
+Gates (north_star): logits and gradients within 2e-2 relative; every parameter tensor with more than 4096 elements is
+held to 2e-2 individually."""
 import pytest
 import torch
 
@@ -47,7 +53,48 @@ def test_bf16_path_matches_fp32_path(tag, kw, batch):
     flat32 = torch.cat([g32[k].double().flatten() for k in g32])
     assert rel_err(flat16, flat32) < 2e-2
     worst = max((rel_err(g16[k], g32[k]), k) for k in g32 if g32[k].numel() > 4096)
-    assert worst[0] < 3e-2, worst
+    assert worst[0] < 2e-2, worst
+
+
+ORACLE_CASES = [
+    ("c2_small_n2049_d384_h6", dict(n_trials=8, freq_size=128, time_size=256, embed_dim=384, n_heads=6, n_layers=2), 1),
+    ("c5_large_n2049_d768_h12", dict(n_trials=8, freq_size=128, time_size=256, embed_dim=768, n_heads=12, n_layers=1), 1),
+    ("realdata_8x64x488_n1953", dict(n_trials=8, freq_size=64, time_size=488, embed_dim=384, n_heads=6, n_layers=1), 2),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag,kw,batch", ORACLE_CASES, ids=[c[0] for c in ORACLE_CASES])
+def test_baseline_shapes_against_fp64_oracle(tag, kw, batch, precision):
+    kw = dict(kw, dropout=0.0, attention_dropout=0.0, drop_path=0.0)
+    cfg = nv.Temporal3DViTConfig(**kw)
+    params = O.random_params(O.config_from(cfg), seed=31)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(batch, cfg.n_trials, cfg.freq_size, cfg.time_size, generator=g).to(DEV)
+    y = torch.randint(0, 2, (batch,), generator=g).to(DEV)
+    m = nv.Temporal3DViT(cfg, precision=precision)
+    m.load_state_dict(params)
+    m.to(DEV).train()
+    logits = m(x)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    del m
+    p64 = {k: v.double().to(DEV) for k, v in params.items()}
+    rl, rloss, rg = O.loss_and_grads(x.double(), y, p64, O.config_from(cfg))
+    if precision == "fp32":
+        assert abs(float(loss) - float(rloss)) <= 1e-4
+        assert rel_err(logits, rl) < 1e-4
+        worst = max((rel_err(grads[k], rg[k]), k) for k in rg)
+        assert worst[0] < 1e-3, worst
+        return
+    assert rel_err(logits, rl) < 2e-2
+    flat = torch.cat([grads[k].double().flatten() for k in rg])
+    flat_ref = torch.cat([rg[k].double().flatten() for k in rg])
+    assert rel_err(flat, flat_ref) < 2e-2
+    errs = sorted(((rel_err(grads[k], rg[k]), k, grads[k].numel()) for k in rg), reverse=True)
+    for e, k, n in errs:
+        assert e < (2e-2 if n > 4096 else 4e-2), errs[:6]
 
 
 def test_batch_of_one_and_odd_batch():

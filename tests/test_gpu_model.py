@@ -94,12 +94,12 @@ def test_against_fp64_oracle(tag, kw, batch, precision):
     if precision == "fp32":
         assert errs[0][0] < tol, errs[:6]
         return
-    # bf16 gate (north_star): logits and the gradient as a whole (all parameters concatenated) within 2e-2.
-    # Per tensor: at the two realistic widths every weight matrix is also within 2e-2 (measured < 1e-2); the
-    # third case is adversarial on purpose (3 layers of D = 128 with O(1) LayerScale, 3 samples of 129 tokens) and
-    # sits at the error floor of bf16 activation storage -- the SIMT bf16 engine with exact erf and fp32 attention
-    # math measures 1.9e-2 on the same matrices -- so there, and for vectors of a few hundred elements that are
-    # dominated by a handful of entries, each tensor is held to 4e-2 (measured values: DESIGN.md section 7).
+    # bf16 gate (north_star): logits and the gradient as a whole (all parameters concatenated) within 2e-2, and every
+    # parameter tensor with more than 4096 elements within 2e-2 individually at the realistic widths (measured
+    # < 1e-2).  STATED EXCEPTION (README): the third case is adversarial on purpose (3 layers of
+    # D = 128 with O(1) LayerScale, 3 samples of 129 tokens) and sits at the error floor of bf16 activation storage --
+    # the SIMT bf16 engine with exact erf and fp32 attention math measures 1.9e-2 on the same matrices -- so there,
+    # and for vectors of <= 4096 elements that are dominated by a handful of entries, each tensor is held to 4e-2.
     flat = torch.cat([grads[k].double().flatten() for k in rg])
     flat_ref = torch.cat([rg[k].double().flatten() for k in rg])
     assert rel_err(flat, flat_ref) < BF16_TOL
