@@ -1,25 +1,34 @@
 #!/usr/bin/env python
 """Benchmark of the Temporal 3D ViT training hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--dropout p]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--impl reference] ...
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path over one synthetic batch exactly as the reference loop drives it
-(train.py:223-227): zero_grad, forward, class-weighted CrossEntropy, backward (+ bucketed gradient
+(train.py:223-227): zero_grad, forward, class-weighted label-smoothed CrossEntropy, backward (+ bucketed gradient
 all-reduce at N > 1) and the AdamW update.  Metric: train samples/sec (BASELINE.json), whole job.
 
-Workload (N = 1): BASELINE.json configs[1] -- default "small" Temporal 3D ViT (D384/H6/L8), input
-8 x 128 x 256 (N = 2049 tokens), batch 256 per GPU, bf16 tensor-core path, reference-default dropout
-rates (0.1/0.1/0.1), synthetic WT/FMR1 labels.  N > 1 keeps the per-GPU batch (weak scaling).
+Workloads (BASELINE.json configs; --config):
+  c2 (default)  small D384/H6/L8, input 8 x 128 x 256 (N = 2049 tokens), batch 256 per GPU        <- the headline
+  c3            depth-12 variant of c2, batch 256 per GPU
+  c4            long sequence 32 x 128 x 512 (N = 16385 tokens), small model, batch 8 per GPU
+  c5            large D768/H12/L24, batch 64 per GPU
+  c1            c2's model at batch 8 (the reference's CPU-runnable case; used by the CPU legs)
+All in bf16 on the tensor-core path with the reference-default dropout rates (0.1/0.1/0.1) and synthetic WT/FMR1
+labels; N > 1 keeps the per-GPU batch (weak scaling).
 
-One JSON line on stdout (rank 0).  `value` has inputs resident in HBM; `e2e` goes through the public
-module call with pinned host inputs copied H2D and the loss read back D2H inside the timed region.
-`--impl reference` times the oracle port of the reference (PyTorch fp32 on the host cores) on a
-bounded sample of the same workload.
+One JSON line on stdout (rank 0).  `value` has inputs resident in HBM; `e2e` goes through the package's public API
+(DevicePrefetcher -> Temporal3DViT -> CrossEntropyLoss -> FusedAdamW) with pinned host inputs copied H2D and the loss
+read back D2H every step inside the timed region.  Extra objects: `roofline` (dominant kernel, CUDA-event timed
+inside the step), `cpu_baseline` (the reference module on the host cores, bounded sample), `gpu_eager_baseline`
+(the reference arithmetic in CUDA eager on the same GPU: the kernel-level comparator).
+`--impl reference` times the reference's own CPU implementation (the unmodified reference module from baseline/_ref
+when installed, else the oracle port) on the host cores on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -36,7 +45,26 @@ if ROOT not in sys.path:
 
 METRIC = "train samples/sec fwd+bwd"
 UNIT = "samples/s"
-WORKLOAD = "small D384/H6/L8, 8x128x256 (N=2049 tokens), batch 256 per GPU, bf16, dropout 0.1/0.1/0.1"
+
+CONFIGS = {
+    "c1": dict(trials=8, freq=128, time=256, embed_dim=384, heads=6, layers=8, batch=8),
+    "c2": dict(trials=8, freq=128, time=256, embed_dim=384, heads=6, layers=8, batch=256),
+    "c3": dict(trials=8, freq=128, time=256, embed_dim=384, heads=6, layers=12, batch=256),
+    "c4": dict(trials=32, freq=128, time=512, embed_dim=384, heads=6, layers=8, batch=8),
+    "c5": dict(trials=8, freq=128, time=256, embed_dim=768, heads=12, layers=24, batch=64),
+}
+CONFIG_NAMES = {
+    "c1": "BASELINE configs[0]: small, batch 8 (CPU case)", "c2": "BASELINE configs[1]: small, batch 256",
+    "c3": "BASELINE configs[2]: depth 12", "c4": "BASELINE configs[3]: long sequence",
+    "c5": "BASELINE configs[4]: large D768/H12/L24",
+}
+
+
+def workload_string(name, a, dropout):
+    n_tok = (a.trials // 2) * (a.freq // 8) * (a.time // 8) + 1
+    return (f"{name} ({CONFIG_NAMES.get(name, 'custom')}): D{a.embed_dim}/H{a.heads}/L{a.layers}, "
+            f"{a.trials}x{a.freq}x{a.time} (N={n_tok} tokens), batch {a.batch} per GPU, bf16, "
+            f"dropout {dropout}/{dropout}/{dropout}")
 
 
 def flops_per_sample(cfg, with_bwd=True):
@@ -111,24 +139,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def ncu_traffic_bytes(batch, args):
+def ncu_traffic_bytes(name):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
-    capture of the final build (profiles/r1_ncu_attn_final_B256_dropout.json, written by tools/ncu_summary.py); only
-    valid for the shape it was captured on."""
-    if (batch, args.layers, args.embed_dim, args.trials, args.time) != (256, 8, 384, 8, 256):
+    capture (written by tools/ncu_summary.py); only valid for the c2 shape it was captured on."""
+    if name != "c2":
         return None
-    path = os.path.join(ROOT, "profiles", "r1_ncu_attn_final_B256_dropout.json")
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-    try:
-        with open(path) as fh:
-            k = next(e for e in json.load(fh) if "tc_attn_bwd_kernel<1>" in e["kernel"])
-        total = 0.0
-        for m in ("dram_rd", "dram_wr"):
-            v, u = k[m].split()
-            total += float(v) * scale[u]
-        return total
-    except (OSError, KeyError, ValueError, StopIteration):
-        return None
+    for fn in ("r2_ncu_attn_B256_dropout.json", "r1_ncu_attn_final_B256_dropout.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as fh:
+                k = next(e for e in json.load(fh) if "tc_attn_bwd_kernel<1>" in e["kernel"])
+            total = 0.0
+            for m in ("dram_rd", "dram_wr"):
+                v, u = k[m].split()
+                total += float(v) * scale[u]
+            return total
+        except (OSError, KeyError, ValueError, StopIteration):
+            continue
+    return None
 
 
 def load_peaks():
@@ -141,46 +169,132 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port of the reference on the host cores
+# the reference's own implementation (checker side): unmodified module from baseline/_ref, else the oracle port
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(cfg_kwargs, sample_batch, steps, warmup, seed=0):
-    """Time `steps` fwd+CE+bwd steps of the oracle (fp32, train mode with the reference-default dropout
-    rates, masks drawn inside the timed region) on a batch of `sample_batch`.  Returns seconds per step."""
+def load_reference_module():
+    path = os.path.join(ROOT, "baseline", "_ref", "temporal_vit", "models", "model.py")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("tvit_reference_model", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["tvit_reference_model"] = mod     # dataclasses resolves cls.__module__ while decorating the config
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def model_kwargs(a, dropout):
+    kw = dict(n_trials=a.trials, freq_size=a.freq, time_size=a.time, embed_dim=a.embed_dim, n_heads=a.heads,
+              n_layers=a.layers)
+    if dropout is not None:
+        kw.update(dropout=dropout, attention_dropout=dropout, drop_path=dropout)
+    return kw
+
+
+def make_reference_step(cfg_kwargs, device, autocast_dtype=None, seed=1234):
+    """Returns (step(x, y) -> loss, kind): fwd + weighted label-smoothed CE + bwd of the reference in train mode with
+    its own nn.Dropout / DropPath (model.py:57-71,102-117; train.py:223-226)."""
+    ref = load_reference_module()
+    cw = torch.tensor([0.8, 1.3], device=device)
+    if ref is not None:
+        torch.manual_seed(seed)
+        model = ref.Temporal3DViT(ref.Temporal3DViTConfig(**cfg_kwargs)).to(device).train()
+        crit = torch.nn.CrossEntropyLoss(weight=cw, label_smoothing=0.05)
+
+        def step(x, y):
+            model.zero_grad(set_to_none=True)
+            if autocast_dtype is not None:
+                with torch.autocast(device_type=torch.device(device).type, dtype=autocast_dtype):
+                    loss = crit(model(x).float(), y)
+            else:
+                loss = crit(model(x), y)
+            loss.backward()
+            return loss
+        return step, "reference"
     from oracle import vit_oracle as O
+    cfg = O.OracleConfig(**cfg_kwargs)
+    params = O.random_params(cfg, seed=seed, device=device)
+    g = torch.Generator(device=device).manual_seed(seed)
+
+    def step(x, y):
+        masks = O.draw_masks(cfg, x.shape[0], generator=g, device=device)
+        if autocast_dtype is not None:
+            with torch.autocast(device_type=torch.device(device).type, dtype=autocast_dtype):
+                return O.loss_and_grads(x, y, params, cfg, class_weight=cw, label_smoothing=0.05, masks=masks)[1]
+        return O.loss_and_grads(x, y, params, cfg, class_weight=cw, label_smoothing=0.05, masks=masks)[1]
+    return step, "port"
+
+
+def cpu_reference_steps(cfg_kwargs, sample_batch, steps, warmup, seed=0):
+    """Time `steps` fwd+CE+bwd steps of the reference on the host cores on a batch of `sample_batch`.
+    Returns (seconds per step, cores, kind)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.OracleConfig(**cfg_kwargs)
-    params = O.random_params(cfg, seed=1234)
+    step, kind = make_reference_step(cfg_kwargs, "cpu")
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(sample_batch, cfg.n_trials, cfg.freq_size, cfg.time_size, generator=g)
+    x = torch.randn(sample_batch, cfg_kwargs["n_trials"], cfg_kwargs["freq_size"], cfg_kwargs["time_size"], generator=g)
     y = torch.randint(0, 2, (sample_batch,), generator=g)
-    cw = torch.tensor([0.8, 1.3])
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        masks = O.draw_masks(cfg, sample_batch, generator=g)
-        O.loss_and_grads(x, y, params, cfg, class_weight=cw, label_smoothing=0.05, masks=masks)
+        step(x, y)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return statistics.median(times), cores
+    return statistics.median(times), cores, kind
 
 
-def run_reference(args, cfg_kwargs):
+def gpu_eager_baseline(cfg_kwargs, dev, steps=3):
+    """The reference arithmetic in CUDA eager on this GPU (SURVEY.md section 8d "kernel to beat"): fp32 as train.py runs
+    it and bf16 autocast, at the largest batch that fits (the (B,H,N,N) score tensors of model.py:111-113 are saved for
+    backward: ~2 GB per sample at the c2 shape)."""
+    out = {}
+    for tag, dt in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        for batch in (64, 32, 16, 8, 4, 2, 1):
+            try:
+                step, kind = make_reference_step(cfg_kwargs, dev, autocast_dtype=dt)
+                x = torch.randn(batch, cfg_kwargs["n_trials"], cfg_kwargs["freq_size"], cfg_kwargs["time_size"],
+                                device=dev)
+                y = torch.randint(0, 2, (batch,), device=dev)
+                step(x, y)
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                for _ in range(steps):
+                    step(x, y)
+                e.record()
+                torch.cuda.synchronize()
+                ms = s.elapsed_time(e) / steps
+                out[tag] = {"value": batch / (ms * 1e-3), "unit": UNIT, "batch": batch, "ms_per_step": ms,
+                            "kind": kind}
+                del step, x, y
+                torch.cuda.empty_cache()
+                break
+            except torch.OutOfMemoryError:
+                step = x = y = None
+                torch.cuda.empty_cache()
+                continue
+    out["note"] = ("reference module (model.py) fwd + CE + bwd in train mode, PyTorch eager on the same GPU, largest "
+                   "power-of-two batch that fits; no optimizer step in its timed region")
+    return out
+
+
+def run_reference(args, cfg_kwargs, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = 1
-    sec, cores = cpu_reference_steps(cfg_kwargs, sample, args.steps, args.warmup)
+    sample = args.cpu_sample
+    sec, cores, kind = cpu_reference_steps(cfg_kwargs, sample, args.steps, args.warmup)
     value = sample / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "host": "cpu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} sample(s) of the batch-256 step per timed step (same per-sample shapes, "
-                                   "train mode, dropout masks drawn in the timed region)"},
+        "config": {"workload": workload, "host": "cpu",
+                   "step": "forward + weighted CE + backward of the reference on the host cores (no optimizer step)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{sample} sample(s) of the workload's per-sample shape per timed step (the full "
+                                   f"per-GPU batch would take minutes per step on {cores} cores), fp32, train mode with "
+                                   "the reference's own nn.Dropout / DropPath inside the timed region; median step"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -197,29 +311,39 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
     ap.add_argument("--dropout", type=float, default=None, help="override all three dropout rates (default: 0.1)")
-    ap.add_argument("--layers", type=int, default=8)
-    ap.add_argument("--embed-dim", type=int, default=384)
-    ap.add_argument("--heads", type=int, default=6)
-    ap.add_argument("--trials", type=int, default=8)
-    ap.add_argument("--freq", type=int, default=128)
-    ap.add_argument("--time", type=int, default=256)
+    ap.add_argument("--layers", type=int, default=None)
+    ap.add_argument("--embed-dim", type=int, default=None)
+    ap.add_argument("--heads", type=int, default=None)
+    ap.add_argument("--trials", type=int, default=None)
+    ap.add_argument("--freq", type=int, default=None)
+    ap.add_argument("--time", type=int, default=None)
+    ap.add_argument("--stock-loop", action="store_true",
+                    help="drive the step with torch.optim.AdamW + torch CrossEntropyLoss (the reference's unchanged "
+                         "loop) instead of FusedAdamW + the device loss")
+    ap.add_argument("--cpu-sample", type=int, default=1, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print a per-op time breakdown to stderr")
     args = ap.parse_args()
-
-    cfg_kwargs = dict(n_trials=args.trials, freq_size=args.freq, time_size=args.time, embed_dim=args.embed_dim,
-                      n_heads=args.heads, n_layers=args.layers)
-    if args.dropout is not None:
-        cfg_kwargs.update(dropout=args.dropout, attention_dropout=args.dropout, drop_path=args.dropout)
+    custom = False
+    for k, v in CONFIGS[args.config].items():
+        if getattr(args, k) is None:
+            setattr(args, k, v)
+        else:
+            custom = custom or getattr(args, k) != v
+    name = args.config if not custom else f"{args.config}*"
+    cfg_kwargs = model_kwargs(args, args.dropout)
+    drop_str = 0.1 if args.dropout is None else args.dropout
+    workload = workload_string(name, args, drop_str)
     if args.impl == "reference":
-        return run_reference(args, cfg_kwargs)
+        return run_reference(args, cfg_kwargs, workload)
 
     import torch.distributed as dist
     import neural_vit_b200 as nv
     from neural_vit_b200 import ops
-    from neural_vit_b200.ddp import BucketedAllReduce
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -233,9 +357,14 @@ def main():
     torch.manual_seed(1234)
     model = nv.Temporal3DViT(cfg, precision="bf16").to(dev)
     model.train()
-    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=0.01)
-    crit = torch.nn.CrossEntropyLoss(weight=torch.tensor([0.8, 1.3], device=dev), label_smoothing=0.05)
-    ddp = BucketedAllReduce(model) if world > 1 else None
+    cw = torch.tensor([0.8, 1.3], device=dev)
+    ddp = nv.BucketedAllReduce(model, measure_exposed=True) if world > 1 else None
+    if args.stock_loop:
+        opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=0.01)
+        crit = torch.nn.CrossEntropyLoss(weight=cw, label_smoothing=0.05)
+    else:
+        opt = nv.FusedAdamW(model.parameters(), lr=3e-4, weight_decay=0.01, model=model)
+        crit = nv.CrossEntropyLoss(weight=cw, label_smoothing=0.05, metrics=nv.DeviceMetrics(dev))
 
     B = args.batch
     g = torch.Generator().manual_seed(rank)
@@ -246,7 +375,7 @@ def main():
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     def step(x, y):
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         logits = model(x)
         loss = crit(logits, y)
         loss.backward()
@@ -260,87 +389,74 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(get_batch, read_loss):
-        for _ in range(args.warmup):
-            loss = step(*get_batch())
-            if read_loss:
-                loss.item()
-        barrier()
-        ops.LAUNCHES["count"] = 0
-        ops.TIMED = {"attn_bwd": []}
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(args.steps):
-            loss = step(*get_batch())
-            if read_loss:
-                loss.item()
-        e.record()
-        barrier()
-        ms = s.elapsed_time(e)
-        timed = ops.TIMED
-        ops.TIMED = None
+    def max_over_ranks(ms):
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
-        return ms, ops.LAUNCHES["count"], timed
+        return ms
 
     # ---- resident-input measurement (value) ----
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    barrier()
+    if ddp is not None:
+        ddp.exposed_events.clear()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_total, launches, timed = timed_loop(lambda: (x_dev, y_dev), read_loss=False)
+    ops.LAUNCHES["count"] = 0
+    ops.TIMED = {"attn_bwd": []}
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        step(x_dev, y_dev)
+    e.record()
+    barrier()
+    ms_total = max_over_ranks(s.elapsed_time(e))
+    launches, timed = ops.LAUNCHES["count"], ops.TIMED
+    ops.TIMED = None
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
-    attn_ms = [s.elapsed_time(e) for s, e in timed["attn_bwd"]]
+    attn_ms = [a.elapsed_time(b) for a, b in timed["attn_bwd"]]
     attn_ms_avg = sum(attn_ms) / max(len(attn_ms), 1)
+    exposed_ms = ddp.exposed_ms() if ddp is not None else 0.0
+    if hasattr(crit, "metrics") and crit.metrics is not None:
+        crit.metrics.reset()
 
-    # ---- end-to-end measurement: pinned host inputs, H2D inside the timed region, loss read back ----
-    # The input pipeline is the usual double-buffered one: the copy of step k+1's batch from pinned host memory runs
-    # on a side stream while step k computes.  All K copies and all K loss read-backs lie inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [(torch.empty_like(x_dev), torch.empty_like(y_dev)) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-
-    def issue_copy(k):
-        with torch.cuda.stream(copy_stream):
-            bufs[k % 2][0].copy_(x_host, non_blocking=True)
-            bufs[k % 2][1].copy_(y_host, non_blocking=True)
-            ready[k % 2].record(copy_stream)
+    # ---- end-to-end measurement through the package's public API: the input feed (DevicePrefetcher: pinned host
+    # batch -> async H2D on a side stream, double buffered) + model + loss + optimizer, loss read back every step ----
+    def host_batches(n):
+        for _ in range(n):
+            yield x_host, y_host
 
     def e2e_steps(n):
-        issue_copy(0)
-        for k in range(n):
-            torch.cuda.current_stream().wait_event(ready[k % 2])
-            if k + 1 < n:
-                issue_copy(k + 1)  # buffer (k+1) % 2 was last read by step k-1, which loss.item() has synchronised
-            step(*bufs[k % 2]).item()
+        feed = nv.DevicePrefetcher(host_batches(n), dev)
+        for xb, yb in feed:
+            step(xb, yb).item()
+        return feed.h2d_bytes
 
     e2e_steps(args.warmup)
     barrier()
     s_e, e_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s_e.record()
-    e2e_steps(args.steps)
+    h2d = e2e_steps(args.steps)
     e_e.record()
     barrier()
-    ms_e2e = s_e.elapsed_time(e_e)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = t.item()
+    ms_e2e = max_over_ranks(s_e.elapsed_time(e_e))
     e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
 
     breakdown = None
     if args.breakdown and rank == 0:
-        names = ["attn_fwd", "attn_bwd"] + [f"gemm_e{i}" for i in range(6)] + ["gemm_e4_tn"]
+        names = ["attn_fwd", "attn_bwd"] + [f"gemm_e{i}" for i in range(7)] + ["gemm_e4_tn"]
         ops.TIMED = {n: [] for n in names}
         if os.environ.get("TVIT_BENCH_DETAIL"):
             ops.TIMED = {"detail": []}
         step(x_dev, y_dev)
         torch.cuda.synchronize()
-        breakdown = {n: (round(sum(s.elapsed_time(e) for s, e in v), 3), len(v)) if "detail" in ops.TIMED
-                     else round(sum(s.elapsed_time(e) for s, e in v), 3) for n, v in ops.TIMED.items() if v}
+        breakdown = {n: (round(sum(a.elapsed_time(b) for a, b in v), 3), len(v)) if "detail" in ops.TIMED
+                     else round(sum(a.elapsed_time(b) for a, b in v), 3) for n, v in ops.TIMED.items() if v}
         ops.TIMED = None
         print("per-op ms in one step:", json.dumps(breakdown), file=sys.stderr)
 
@@ -353,36 +469,45 @@ def main():
     fl_step = flops_per_sample(cfg) * B            # per GPU
     model_tflops = fl_step / (ms_step * 1e-3) / 1e12
     attn_tflops = attn_bwd_flops(cfg, B) / (attn_ms_avg * 1e-3) / 1e12 if attn_ms_avg > 0 else 0.0
+    step_desc = ("zero_grad + forward + weighted CE + backward" + (" + bucketed NCCL all-reduce (AVG, grads written "
+                 "straight into the buckets)" if world > 1 else "") + " + AdamW; "
+                 + ("torch.optim.AdamW + torch CE (stock loop)" if args.stock_loop
+                    else "FusedAdamW + device CE/metrics (this package)"))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD if (B, args.layers, args.embed_dim, args.dropout, args.trials, args.time) ==
-                   (256, 8, 384, None, 8, 256)
-                   else f"D{args.embed_dim}/H{args.heads}/L{args.layers}, {args.trials}x{args.freq}x{args.time}, "
-                        f"batch {B} per GPU, bf16, dropout {cfg.dropout}",
-                   "step": "zero_grad + forward + weighted CE + backward" + (" + bucketed NCCL all-reduce" if world > 1 else "")
-                           + " + AdamW", "global_batch": world * B, "tokens_per_sample": cfg.n_patches + 1,
-                   "parallelism": f"dp{world}", "l2": "per-step working set (>= 268 MB input, tens of GB of activations) exceeds the 126 MB L2"},
+        "config": {"workload": workload, "step": step_desc, "global_batch": world * B,
+                   "tokens_per_sample": cfg.n_patches + 1, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (>= 268 MB input, tens of GB of activations) exceeds the 126 MB L2"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
-                "d2h_bytes_per_step": 4},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "model_tflops_per_gpu": model_tflops,
         "model_frac_of_peak": model_tflops / sustained,
         "roofline": {"bound": "tensor", "kernel": "tc_attn_bwd_kernel (+prep/finish)", "achieved": attn_tflops,
                      "peak": sustained, "peak_kind": f"{which} sustained cuBLAS bf16", "unit": "TFLOP/s",
                      "frac": attn_tflops / sustained, "ms_per_launch": attn_ms_avg, "launches_timed": len(attn_ms),
-                     "traffic": ncu_traffic_bytes(B, args)},
+                     "traffic": ncu_traffic_bytes(name)},
     }
+    if world > 1:
+        line["allreduce_exposed_ms_per_step"] = exposed_ms
     if breakdown:
         line["breakdown_ms"] = breakdown
     if world == 1 and not args.no_cpu_baseline:
-        sample = 1
-        sec, cores = cpu_reference_steps(cfg_kwargs, sample, steps=2, warmup=1)
-        line["cpu_baseline"] = {"value": sample / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{sample} sample(s) per step of the same per-sample shapes, fp32 oracle, train "
-                                          "mode with dropout masks drawn in the timed region; median of 2 steps"}
+        sample = args.cpu_sample
+        sec, cores, kind = cpu_reference_steps(cfg_kwargs, sample, steps=2, warmup=1)
+        line["cpu_baseline"] = {"value": sample / sec, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"{sample} sample(s) of the workload's per-sample shape per step, fp32, train "
+                                          "mode with the reference's own dropout inside the timed region; forward + CE + "
+                                          "backward; median of 2 steps after 1 warm-up"}
+    if world == 1 and not args.no_eager_baseline:
+        del x_dev, y_dev
+        torch.cuda.empty_cache()
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(cfg_kwargs, dev)
+        except Exception as exc:  # the comparator must never take the measurement down with it
+            line["gpu_eager_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

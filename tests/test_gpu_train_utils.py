@@ -87,7 +87,13 @@ def test_fused_adamw_matches_torch_adamw_and_refreshes_shadows(precision):
                     want_t = (w.detach() if gamma is None else gamma.detach()[:, None] * w.detach()).t().bfloat16()
                     assert torch.equal(wt_sh, want_t), (step, i, name)
     tol = 2e-4 if precision == "fp32" else 3e-2      # bf16: the two runs see differently-ordered bf16 rounding
+    D = a.config.embed_dim
     for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        if k.endswith("attn.qkv.bias"):
+            # softmax is invariant to a shift of the scores along the key axis, so the gradient of the K third of
+            # the qkv bias is exactly zero in exact arithmetic; what each run sees there is rounding noise that Adam
+            # normalises to O(lr) steps of random sign.  Compare the Q and V thirds.
+            pa, pb = torch.cat([pa[:D], pa[2 * D:]]), torch.cat([pb[:D], pb[2 * D:]])
         assert rel_err(pb, pa) < tol, k
     # same loss on a fresh batch => the forward really uses the updated (adopted) operands
     x, y = _data(a.config, 8, seed=99)
