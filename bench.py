@@ -191,23 +191,27 @@ def model_kwargs(a, dropout):
 
 
 def make_reference_step(cfg_kwargs, device, autocast_dtype=None, seed=1234):
-    """Returns (step(x, y) -> loss, kind): fwd + weighted label-smoothed CE + bwd of the reference in train mode with
-    its own nn.Dropout / DropPath (model.py:57-71,102-117; train.py:223-226)."""
+    """Returns (step(x, y) -> loss, kind): zero_grad + fwd + weighted label-smoothed CE + bwd + AdamW of the reference
+    in train mode with its own nn.Dropout / DropPath (model.py:57-71,102-117; train.py:223-227).  kind "reference" =
+    the unmodified reference module; "port" (only when baseline/_ref is absent) = the oracle restatement, fwd + CE +
+    bwd with masks drawn in the timed region."""
     ref = load_reference_module()
     cw = torch.tensor([0.8, 1.3], device=device)
     if ref is not None:
         torch.manual_seed(seed)
         model = ref.Temporal3DViT(ref.Temporal3DViTConfig(**cfg_kwargs)).to(device).train()
         crit = torch.nn.CrossEntropyLoss(weight=cw, label_smoothing=0.05)
+        opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=0.01)      # train.py:154-156
 
-        def step(x, y):
-            model.zero_grad(set_to_none=True)
+        def step(x, y):                                                               # train.py:223-227
+            opt.zero_grad()
             if autocast_dtype is not None:
                 with torch.autocast(device_type=torch.device(device).type, dtype=autocast_dtype):
                     loss = crit(model(x).float(), y)
             else:
                 loss = crit(model(x), y)
             loss.backward()
+            opt.step()
             return loss
         return step, "reference"
     from oracle import vit_oracle as O
@@ -273,8 +277,8 @@ def gpu_eager_baseline(cfg_kwargs, dev, steps=3):
                 step = x = y = None
                 torch.cuda.empty_cache()
                 continue
-    out["note"] = ("reference module (model.py) fwd + CE + bwd in train mode, PyTorch eager on the same GPU, largest "
-                   "power-of-two batch that fits; no optimizer step in its timed region")
+    out["note"] = ("reference module (model.py) zero_grad + fwd + CE + bwd + AdamW in train mode, PyTorch eager on the "
+                   "same GPU, largest power-of-two batch that fits")
     return out
 
 
@@ -290,7 +294,7 @@ def run_reference(args, cfg_kwargs, workload):
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "host": "cpu",
-                   "step": "forward + weighted CE + backward of the reference on the host cores (no optimizer step)"},
+                   "step": "zero_grad + forward + weighted CE + backward + AdamW of the reference on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{sample} sample(s) of the workload's per-sample shape per timed step (the full "
                                    f"per-GPU batch would take minutes per step on {cores} cores), fp32, train mode with "
@@ -499,8 +503,8 @@ def main():
         sec, cores, kind = cpu_reference_steps(cfg_kwargs, sample, steps=2, warmup=1)
         line["cpu_baseline"] = {"value": sample / sec, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"{sample} sample(s) of the workload's per-sample shape per step, fp32, train "
-                                          "mode with the reference's own dropout inside the timed region; forward + CE + "
-                                          "backward; median of 2 steps after 1 warm-up"}
+                                          "mode with the reference's own dropout inside the timed region; the full "
+                                          "step (fwd + CE + bwd + AdamW); median of 2 steps after 1 warm-up"}
     if world == 1 and not args.no_eager_baseline:
         del x_dev, y_dev
         torch.cuda.empty_cache()
