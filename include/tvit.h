@@ -66,12 +66,14 @@ int tvit_device_check(int device);
 enum {
   /* out[T][m,n] = acc + bias[n] */
   TVIT_EPI_STORE = 0,
-  /* h = acc + bias[n]; aux[T][m,n] = h; out[T][m,n] = dropout(gelu_erf(h))        (fc1, :143-145) */
+  /* h = acc + bias[n]; out[T][m,n] = dropout(gelu_erf(h))                         (fc1, :143-145)
+   * aux[T][m,n] = dropout_mult(m,n) * gelu_erf'(h): d out / d h, i.e. everything the backward of this site needs, so
+   * that neither the pre-activation nor the mask has to be re-derived in backward */
   TVIT_EPI_BIAS_GELU = 1,
   /* out_f32[m,n] = resid[m,n] + row_scale[m / rows_per_group] * gamma[n] * dropout(acc + bias[n])
    * (proj/fc2 + proj_drop/drop2 + LayerScale + DropPath + residual, :116-117,:146-147,:82,:67-71,:176-177) */
   TVIT_EPI_RESIDUAL = 2,
-  /* out[T][m,n] = acc * dropout_mult(m,n) * gelu'(aux[T][m,n])                  (backward of fc1's GELU/drop1) */
+  /* out[T][m,n] = acc * aux[T][m,n], aux as written by BIAS_GELU              (backward of fc1's GELU/drop1) */
   TVIT_EPI_GELU_BWD = 3,
   /* out_f32[m,n] += acc  (atomic; caller zero-fills).  Weight gradients, split along K.  */
   TVIT_EPI_ACCUM_F32 = 4,
@@ -96,7 +98,7 @@ typedef struct {
   void* out;
   long long ldo;
   const float* bias; /* [N] or NULL */
-  void* aux;         /* BIAS_GELU: pre-activation out; GELU_BWD: pre-activation in */
+  void* aux;         /* BIAS_GELU: d out / d pre-activation (out); GELU_BWD: the same tensor (in) */
   long long ldaux;
   const float* resid; /* RESIDUAL */
   long long ldres;

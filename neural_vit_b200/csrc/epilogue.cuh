@@ -98,8 +98,9 @@ __device__ __forceinline__ void epi_apply1(const EpiParams& p, int m, int n, flo
     Act<T>::st((T*)p.out + m * p.ldo + n, v);
   } else if (EPI == TVIT_EPI_BIAS_GELU) {
     if (p.bias) v += p.bias[n];
-    Act<T>::st((T*)p.aux + m * p.ldaux + n, v);
-    Act<T>::st((T*)p.out + m * p.ldo + n, gelu_t<T>(v) * drop_mult(p.drop, (unsigned long long)m * p.N + n));
+    const float mlt = drop_mult(p.drop, (unsigned long long)m * p.N + n);
+    Act<T>::st((T*)p.aux + m * p.ldaux + n, gelu_grad_t<T>(v) * mlt);
+    Act<T>::st((T*)p.out + m * p.ldo + n, gelu_t<T>(v) * mlt);
   } else if (EPI == TVIT_EPI_RESIDUAL) {
     if (p.bias) v += p.bias[n];
     v *= drop_mult(p.drop, (unsigned long long)m * p.N + n);
@@ -107,8 +108,7 @@ __device__ __forceinline__ void epi_apply1(const EpiParams& p, int m, int n, flo
     if (p.row_scale) v *= p.row_scale[m / p.rpg];
     ((float*)p.out)[m * p.ldo + n] = p.resid[m * p.ldres + n] + v;
   } else if (EPI == TVIT_EPI_GELU_BWD) {
-    const float h = Act<T>::ld((const T*)p.aux + m * p.ldaux + n);
-    Act<T>::st((T*)p.out + m * p.ldo + n, v * drop_mult(p.drop, (unsigned long long)m * p.N + n) * gelu_grad_t<T>(h));
+    Act<T>::st((T*)p.out + m * p.ldo + n, v * Act<T>::ld((const T*)p.aux + m * p.ldaux + n));
   } else if (EPI == TVIT_EPI_ACCUM_F32) {
     atomicAdd((float*)p.out + m * p.ldo + n, v);
   } else if (EPI == TVIT_EPI_SOFTMAX_PROBS) {
@@ -146,9 +146,11 @@ __device__ __forceinline__ void epi_apply4(const EpiParams& p, int m, int n0, fl
       const float4 b = ld4(p.bias + n0);
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
-    st4((T*)p.aux + m * p.ldaux + n0, v);
     float mlt[4];
     drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, mlt);
+    st4((T*)p.aux + m * p.ldaux + n0,
+        make_float4(gelu_grad_t<T>(v.x) * mlt[0], gelu_grad_t<T>(v.y) * mlt[1], gelu_grad_t<T>(v.z) * mlt[2],
+                    gelu_grad_t<T>(v.w) * mlt[3]));
     st4((T*)p.out + m * p.ldo + n0,
         make_float4(gelu_t<T>(v.x) * mlt[0], gelu_t<T>(v.y) * mlt[1], gelu_t<T>(v.z) * mlt[2], gelu_t<T>(v.w) * mlt[3]));
   } else if (EPI == TVIT_EPI_RESIDUAL) {
@@ -166,11 +168,7 @@ __device__ __forceinline__ void epi_apply4(const EpiParams& p, int m, int n0, fl
                     r.w + rs * g.w * v.w * mlt[3]));
   } else if (EPI == TVIT_EPI_GELU_BWD) {
     const float4 h = ld4((const T*)p.aux + m * p.ldaux + n0);
-    float mlt[4];
-    drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, mlt);
-    st4((T*)p.out + m * p.ldo + n0,
-        make_float4(v.x * mlt[0] * gelu_grad_t<T>(h.x), v.y * mlt[1] * gelu_grad_t<T>(h.y), v.z * mlt[2] * gelu_grad_t<T>(h.z),
-                    v.w * mlt[3] * gelu_grad_t<T>(h.w)));
+    st4((T*)p.out + m * p.ldo + n0, make_float4(v.x * h.x, v.y * h.y, v.z * h.z, v.w * h.w));
   } else if (EPI == TVIT_EPI_ACCUM_F32) {
     float* o = (float*)p.out + m * p.ldo + n0;
     atomicAdd(o + 0, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
@@ -218,10 +216,13 @@ __device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, co
       *reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + m * p.ldo + n0) = o;
       return;
     }
-    float ml[8];
-    drop_mult8(p.drop, (unsigned long long)m * p.N + n0, ml);  // vec8_ok: N % 8 == 0 and n0 % 8 == 0
     if (EPI == TVIT_EPI_BIAS_GELU) {
-      uint4 h = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+      float ml[8];
+      drop_mult8(p.drop, (unsigned long long)m * p.N + n0, ml);  // vec8_ok: N % 8 == 0 and n0 % 8 == 0
+      float d[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = gelu_grad_t<T>(x[j]) * ml[j];
+      uint4 h = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
       *reinterpret_cast<uint4*>((__nv_bfloat16*)p.aux + m * p.ldaux + n0) = h;
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = gelu_t<T>(x[j]) * ml[j];
@@ -231,8 +232,8 @@ __device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, co
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
-        x[2 * j] = x[2 * j] * ml[2 * j] * gelu_grad_t<T>(f.x);
-        x[2 * j + 1] = x[2 * j + 1] * ml[2 * j + 1] * gelu_grad_t<T>(f.y);
+        x[2 * j] *= f.x;
+        x[2 * j + 1] *= f.y;
       }
     }
     uint4 o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
@@ -316,60 +317,90 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   if (!row_ok) return;
 
-  float x[16];
+  // All arithmetic below is packed fp32x2 (FFMA2 / FMUL2 / FADD2: two fp32 results per issue slot, bit-identical per
+  // lane to the scalar instructions): at K = 384 the epilogue has ~12 issue slots per output element before it,
+  // not the MMA, sets the pace of the kernel.
+  f32x2 x[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(acc[j]);
+  for (int j = 0; j < 8; ++j) x[j] = pk2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
   if (kBias) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      x[4 * j] += b[j].x; x[4 * j + 1] += b[j].y; x[4 * j + 2] += b[j].z; x[4 * j + 3] += b[j].w;
+      x[2 * j] = add2(x[2 * j], pk2(b[j].x, b[j].y));
+      x[2 * j + 1] = add2(x[2 * j + 1], pk2(b[j].z, b[j].w));
     }
   }
   if (EPI == TVIT_EPI_STORE) {
-    st_bf16x16((__nv_bfloat16*)p.out + m * p.ldo + nc, x);
-    return;
-  }
-  // bf16 outputs: the dropout keep masks are applied to packed bf16 pairs (one Philox call, then two prmt and an
-  // integer subtract per pair), the 1/(1-p) factor is one multiply; fp32 outputs use per-element multipliers.
-  const float keep_scale = kDrop ? p.drop.inv_keep : 1.0f;
-  if (EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_GELU_BWD) {
-    uint32_t mk[8];
-    if (kDrop) drop_keep_masks16(p.drop, (unsigned long long)m * p.N + nc, mk);  // vec16_ok: N, nc % 16 == 0
     uint32_t v[8];
-    if (EPI == TVIT_EPI_BIAS_GELU) {
-      st_bf16x16((__nv_bfloat16*)p.aux + m * p.ldaux + nc, x);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        v[j] = pack_bf16(gelu_fast(x[2 * j]) * keep_scale, gelu_fast(x[2 * j + 1]) * keep_scale);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ext[j]));
-        v[j] = pack_bf16(x[2 * j] * keep_scale * gelu_grad_fast(f.x), x[2 * j + 1] * keep_scale * gelu_grad_fast(f.y));
-      }
-    }
-    if (kDrop) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] &= mk[j];
+    for (int j = 0; j < 8; ++j) {
+      float lo, hi;
+      up2(x[j], lo, hi);
+      v[j] = pack_bf16(lo, hi);
     }
     st_global_v8((__nv_bfloat16*)p.out + m * p.ldo + nc, v);
     return;
   }
-  float ml[16];
-  if (kDrop) {
-    drop_mult16(p.drop, (unsigned long long)m * p.N + nc, ml);  // vec16_ok: N % 16 == 0 and nc % 16 == 0
-  } else {
+  if (EPI == TVIT_EPI_BIAS_GELU) {
+    // out = drop(gelu(h)),  aux = dropmask/(1-p) * gelu'(h): the factor the backward GEMM's epilogue multiplies by, so
+    // GELU_BWD needs neither the activation derivative nor the mask generator.  bf16 outputs: the keep masks are
+    // applied to packed bf16 pairs (one Philox call, then two prmt and an integer subtract per pair).
+    uint32_t mk[8];
+    if (kDrop) drop_keep_masks16(p.drop, (unsigned long long)m * p.N + nc, mk);  // vec16_ok: N, nc % 16 == 0
+    const float ks = kDrop ? p.drop.inv_keep : 1.0f;
+    uint32_t v[8], dv[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) ml[j] = 1.0f;  // folded away by the compiler
+    for (int j = 0; j < 8; ++j) {
+      float x0, x1;
+      up2(x[j], x0, x1);
+      f32x2 y, d;
+      gelu_fast2<true, kDrop>(x0, x1, ks, y, d);
+      float y0, y1, d0, d1;
+      up2(y, y0, y1);
+      up2(d, d0, d1);
+      v[j] = pack_bf16(y0, y1);
+      dv[j] = pack_bf16(d0, d1);
+      if (kDrop) {
+        v[j] &= mk[j];
+        dv[j] &= mk[j];
+      }
+    }
+    st_global_v8((__nv_bfloat16*)p.aux + m * p.ldaux + nc, dv);
+    st_global_v8((__nv_bfloat16*)p.out + m * p.ldo + nc, v);
+    return;
+  }
+  if (EPI == TVIT_EPI_GELU_BWD) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ext[j]));
+      float o0, o1;
+      up2(mul2(x[j], pk2(f.x, f.y)), o0, o1);
+      v[j] = pack_bf16(o0, o1);
+    }
+    st_global_v8((__nv_bfloat16*)p.out + m * p.ldo + nc, v);
+    return;
   }
   if (EPI == TVIT_EPI_RESIDUAL) {
+    // out = resid + (row_scale * gamma) * (dropout multiplier * (acc + bias))
+    float ml[16];
+    if (kDrop) drop_mult16(p.drop, (unsigned long long)m * p.N + nc, ml);  // vec16_ok: N % 16 == 0 and nc % 16 == 0
     float* o = (float*)p.out + m * p.ldo + nc;
+    const f32x2 rs2 = pk2(row_scale, row_scale);
     const float gg[16] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w,
                           g[2].x, g[2].y, g[2].z, g[2].w, g[3].x, g[3].y, g[3].z, g[3].w};
     uint32_t ov[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      ov[j] = __float_as_uint(fmaf(row_scale * gg[j], x[j] * ml[j], __uint_as_float(ext[j])));
+    for (int j = 0; j < 8; ++j) {
+      f32x2 v = x[j];
+      if (kDrop) v = mul2(v, pk2(ml[2 * j], ml[2 * j + 1]));
+      const f32x2 r = fma2(mul2(rs2, pk2(gg[2 * j], gg[2 * j + 1])), v,
+                           pk2(__uint_as_float(ext[2 * j]), __uint_as_float(ext[2 * j + 1])));
+      float r0, r1;
+      up2(r, r0, r1);
+      ov[2 * j] = __float_as_uint(r0);
+      ov[2 * j + 1] = __float_as_uint(r1);
+    }
     st_global_v8(o, *reinterpret_cast<uint32_t(*)[8]>(&ov[0]));
     st_global_v8(o + 8, *reinterpret_cast<uint32_t(*)[8]>(&ov[8]));
   }

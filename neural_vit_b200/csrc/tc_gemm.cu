@@ -468,8 +468,7 @@ static int launch_tc_d(const tvit_gemm_args* a, const GemmShape& sh, const EpiPa
 
 template <int BN, bool MN, int EPI>
 static int launch_tc(const tvit_gemm_args* a, const GemmShape& sh, const EpiParams& ep, cudaStream_t s) {
-  constexpr bool kCanDrop = (EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_GELU_BWD ||
-                             EPI == TVIT_EPI_PATCH_EMBED);
+  constexpr bool kCanDrop = (EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_PATCH_EMBED);
   // weight-stationary variant: K-major, K <= 384, BN = 192 divides N, enough m-tiles to keep every CTA busy
   constexpr bool kResOk = (BN == 192) && !MN &&
                           (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL ||

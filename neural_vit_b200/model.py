@@ -279,7 +279,7 @@ def _block_forward(h, n1w, n1b, qkvw, qkvb, pw, pb, g1, n2w, n2b, f1w, f1b, f2w,
     y2 = _empty((M, D), td, dev)
     mean2, rstd2 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
     ops.ln_fwd(h_mid, D, n2w, n2b, y2, T, mean2, rstd2, M, D)
-    hpre = _empty((M, hid), td, dev)
+    hpre = _empty((M, hid), td, dev)   # d act / d pre-activation (GELU' x dropout multiplier), consumed by GELU_BWD
     act = _empty((M, hid), td, dev)
     ops.gemm(E, T, y2, fc1_w, M, hid, D, epilogue=L.EPI_BIAS_GELU, out=act, aux=hpre, bias=f1b, drop=d_fc1)
     h_out = torch.empty_like(h)
@@ -333,7 +333,7 @@ class _BlockFn(torch.autograd.Function):
             cs2, _ = _dst(sk, I_F2B, (D,), dev)            # without LayerScale colsum(gp) IS the bias gradient
         ops.branch_grad_prep(g_out, M, D, s2, N, d_fc2, gp2, T, cs2)
         dh = _empty((M, hid), td, dev)   # grad wrt fc1 pre-activation
-        ops.gemm(E, T, gp2, fc2_wt, M, hid, D, epilogue=L.EPI_GELU_BWD, out=dh, aux=hpre, drop=d_fc1)
+        ops.gemm(E, T, gp2, fc2_wt, M, hid, D, epilogue=L.EPI_GELU_BWD, out=dh, aux=hpre)
         if ctx.has_ls:
             G2 = _zeros((D, hid), dev)
         else:
@@ -443,8 +443,7 @@ class _HeadFn(torch.autograd.Function):
         d_b3, _ = _dst(sk, 5, (C,), dev)
         ops.colsum(dlogits, T, B, C, C, d_b3)
         dzpre = _empty((B, D), f32, dev)   # (dlogits @ w3) * drop * gelu'(zpre)
-        ops.gemm(E, T, dlogits, w3.detach(), B, D, C, epilogue=L.EPI_GELU_BWD, out=dzpre, aux=zpre, trans_b=True,
-                 drop=ctx.drop)
+        ops.gemm(E, T, dlogits, w3.detach(), B, D, C, epilogue=L.EPI_GELU_BWD, out=dzpre, aux=zpre, trans_b=True)
         d_w0, _ = _dst(sk, 2, (D, D), dev)
         ops.gemm(E, T, dzpre, c, D, D, B, epilogue=L.EPI_ACCUM_F32, out=d_w0, trans_a=True, trans_b=True)
         d_b0, _ = _dst(sk, 3, (D,), dev)

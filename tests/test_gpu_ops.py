@@ -69,9 +69,21 @@ def test_gemm_bias_gelu(engine, dtype, tag):
     td = ops.torch_dtype(dtype)
     out, aux = torch.empty((M, N), dtype=td, device=DEV), torch.empty((M, N), dtype=td, device=DEV)
     ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_BIAS_GELU, out=out, aux=aux, bias=bias)
-    h = a.double() @ b.double().T + bias.double()
-    assert rel_err(aux, h) < _tol(dtype)
-    assert rel_err(out, O.gelu_erf(h)) < _tol(dtype)
+    h = (a.double() @ b.double().T + bias.double()).requires_grad_(True)
+    act = O.gelu_erf(h)
+    act.sum().backward()
+    assert rel_err(out, act) < _tol(dtype)
+    # aux = d out / d h (GELU' here; times the dropout multiplier when dropout is on): what GELU_BWD multiplies by
+    assert rel_err(aux, h.grad) < _tol(dtype)
+    # with dropout both outputs carry the SAME mask and the 1/(1-p) factor
+    drop = (77, 4, 0.25)
+    out_d, aux_d = torch.empty_like(out), torch.empty_like(aux)
+    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_BIAS_GELU, out=out_d, aux=aux_d, bias=bias, drop=drop)
+    keep = aux_d != 0                       # gelu' vanishes nowhere on these inputs (|h| < 6)
+    assert abs(keep.float().mean().item() - 0.75) < 5e-3
+    assert torch.equal(out_d.float()[~keep], torch.zeros_like(out_d.float()[~keep]))
+    assert rel_err(out_d.float()[keep], out.float()[keep] / 0.75) < 2 * _tol(dtype) + 1e-3
+    assert rel_err(aux_d.float()[keep], aux.float()[keep] / 0.75) < 2 * _tol(dtype) + 1e-3
 
 
 @pytest.mark.parametrize("engine,dtype,tag", ENGINES, ids=[e[2] for e in ENGINES])
@@ -97,12 +109,10 @@ def test_gemm_residual_layerscale_droppath(engine, dtype, tag):
 def test_gemm_gelu_bwd(engine, dtype, tag):
     M, N, K = 520, 1536, 384
     a, b = _rand((M, K), dtype, 14), _rand((N, K), dtype, 15, 1 / math.sqrt(K))
-    h = _rand((M, N), dtype, 16)
+    daux = _rand((M, N), dtype, 16)      # d act / d pre-activation as written by the BIAS_GELU epilogue
     out = torch.empty((M, N), dtype=ops.torch_dtype(dtype), device=DEV)
-    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_GELU_BWD, out=out, aux=h)
-    hd = h.double().requires_grad_(True)
-    O.gelu_erf(hd).sum().backward()
-    ref = (a.double() @ b.double().T) * hd.grad
+    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_GELU_BWD, out=out, aux=daux)
+    ref = (a.double() @ b.double().T) * daux.double()
     assert rel_err(out, ref) < _tol(dtype)
 
 
@@ -410,7 +420,7 @@ def test_dropout_mask_matches_numpy_oracle(seed, site, p):
     aux16 = torch.empty_like(out16)
     ops.gemm(L.ENGINE_TCGEN05, L.BF16, a, b, rows, D, 64, epilogue=L.EPI_BIAS_GELU, out=out16, aux=aux16, bias=bias,
              drop=(seed, site, p))
-    assert torch.equal(out16 != 0, ref)
+    assert torch.equal(out16 != 0, ref) and torch.equal(aux16 != 0, ref)
     # attention: V = identity-like probe is not needed -- with q = k = 0 every probability is 1/N, so
     # out[b, q, h, :] = inv_keep / N * sum_k keep(b,h,q,k) v[k]; use v[k] = one-hot(k mod 64) and compare the counts
     Bsz, N, H, hd = 2, 150, 2, 64
