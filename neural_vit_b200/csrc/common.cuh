@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -351,6 +352,18 @@ __device__ __forceinline__ void drop_keep_masks16(const DropCfg& c, unsigned lon
     mk[2 * j] = drop_keep_mask2<0>(w[j], tgc);
     mk[2 * j + 1] = drop_keep_mask2<1>(w[j], tgc);
   }
+}
+
+// Ragged tail of the tcgen05 attention kernels: when N = 128 m + t with 1 <= t <= kMaxAttnTail, the last t keys (forward)
+// / queries (backward) are handled on the CUDA cores instead of through an almost empty 128-wide tile.  TVIT_ATTN_TAIL=0
+// in the environment disables it (debugging / A-B timing).
+constexpr int kMaxAttnTail = 4;
+inline int attn_tail(int N) {
+  // measured at the bench shape (r2_kern_v10*.log): with the tail work at the start / end of each CTA its latency is
+  // exposed and cancels the saved tile, so the path is opt-in (TVIT_ATTN_TAIL=1) until it is moved off the critical path
+  static const bool on = [] { const char* e = getenv("TVIT_ATTN_TAIL"); return e && e[0] == '1'; }();
+  const int t = N % 128;
+  return (on && N > 128 && t >= 1 && t <= kMaxAttnTail) ? t : 0;
 }
 
 // Attention-probability dropout (the N x N site) element index: row-major over (b, h, q, k) with the k extent

@@ -7,6 +7,10 @@
 //                          max / sum in registers, P -> bf16 -> TMEM (tcgen05.st), conditional O rescale
 // The S_{j+1} MMA is issued as soon as S_j has been read into registers, so it overlaps softmax_j; two
 // CTAs per SM (80 KB smem, 256 TMEM columns each) overlap one CTA's exponentials with the other's MMAs.
+// Ragged tail: when N = 128 m + t with a small t (the CLS token makes N = 2049 = 16 * 128 + 1 at the bench shape), the
+// last t keys are NOT given a 17th, almost empty 128-key tile (it cost 1/17 of the kernel); their scores are t dot
+// products per query row, computed by the softmax threads on the CUDA cores from the Q tile in shared memory: they
+// initialise the running max / sum before the tile loop and their P V contribution is added in the epilogue.
 // Only the row log-sum-exp is kept for backward.  qkv is read in place through a 3-D tensor map
 // {3D, N, B} (rows past N are zero-filled by TMA), the output is written token-major [B*N, H*64].
 #include "tc_common.cuh"
@@ -18,6 +22,24 @@ constexpr int kTile = 128;
 constexpr int kAttnFwdThreads = 320;  // warps 0-7 softmax (2 threads per query row), 8 TMA, 9 MMA
 constexpr int kTileBytes = kTile * kHd * 2;  // 16384
 
+// 8 bf16 (one 16-byte piece) -> fp32 dot-product accumulation helpers
+__device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b, float acc) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
+    const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[i]));
+    acc = fmaf(fa.x, fb.x, acc);
+    acc = fmaf(fa.y, fb.y, acc);
+  }
+  return acc;
+}
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
 struct AttnFwdSmem {
   uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, pv_done;
   uint32_t tmem_base;
@@ -26,8 +48,9 @@ struct AttnFwdSmem {
 
 template <bool kDrop>
 __global__ void __launch_bounds__(kAttnFwdThreads, 2)
-tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
-                   float* __restrict__ lse, int N, int H, float scale_log2, DropCfg drop) {
+tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv,
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int tail, int H, float scale_log2,
+                   DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -39,7 +62,8 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int D = H * kHd;
   const int q0 = qt * kTile;
-  const int nkv = (N + kTile - 1) / kTile;
+  const int Nk = N - tail;  // keys covered by 128-key tiles; the remaining `tail` keys go through the CUDA cores
+  const int nkv = (Nk + kTile - 1) / kTile;
 
   if (threadIdx.x == 0) {
     mbar_init(&sm->q_full, 1);
@@ -139,10 +163,43 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
     const int q = q0 + r;
     float m2 = -INFINITY, l = 0.f;
     const unsigned long long rowe = attn_drop_row_base(b, H, h, N, q < N ? q : 0);
+    // raw scores q . k of the tail keys (both partner threads compute all of them).  They are computed twice -- here
+    // and again in the epilogue -- rather than kept in registers across the tile loop (the Q tile stays in smem).
+    auto tail_scores = [&](float (&st)[kMaxAttnTail]) {
+#pragma unroll
+      for (int t = 0; t < kMaxAttnTail; ++t) st[t] = 0.f;
+      const uint32_t qrow = smem_u32(sQ) + (uint32_t)r * 128u;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {  // 16-byte pieces of the 128B-swizzled row
+        const uint4 qa = ld_shared_u4(qrow + (uint32_t)((c ^ (r & 7)) * 16));
+#pragma unroll
+        for (int t = 0; t < kMaxAttnTail; ++t)
+          if (t < tail) {
+            const uint4 kb = __ldg(reinterpret_cast<const uint4*>(
+                qkv + ((long long)b * N + Nk + t) * (3LL * D) + D + h * kHd + 8 * c));
+            st[t] = dot8_bf16(qa, kb, st[t]);
+          }
+      }
+    };
+    if (tail > 0) {
+      mbar_wait(&sm->q_full, 0);  // the Q tile has landed (TMA complete_tx)
+      float st[kMaxAttnTail];
+      tail_scores(st);
+      float mt = st[0];
+#pragma unroll
+      for (int t = 1; t < kMaxAttnTail; ++t)
+        if (t < tail) mt = fmaxf(mt, st[t]);
+      m2 = mt * scale_log2;
+      if (hf == 0) {  // the partners' row sums are added at the end: only one of them may count the tail
+#pragma unroll
+        for (int t = 0; t < kMaxAttnTail; ++t)
+          if (t < tail) l += ex2_approx(fmaf(st[t], scale_log2, -m2));
+      }
+    }
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&sm->s_full, (uint32_t)j & 1u);
       tc_fence_after();
-      const int valid = N - j * kTile - hf * 64;  // keys beyond N are masked (last tile only)
+      const int valid = Nk - j * kTile - hf * 64;  // keys beyond the tiled range are masked (last tile only)
       // ---- pass A: row maximum of this thread's 64 scores ----
       float mx;
       {
@@ -250,6 +307,28 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __
       uint32_t o[32];
       tmem_ld32(tO + lane_off + hf * 32, o);
       tmem_ld_wait();
+      if (tail > 0 && q < N) {  // P V of the tail keys (dropout keep factor included; 1/(1-p) rides on `inv`)
+        float st[kMaxAttnTail];
+        tail_scores(st);
+#pragma unroll
+        for (int t = 0; t < kMaxAttnTail; ++t)
+          if (t < tail) {
+            float pt = ex2_approx(fmaf(st[t], scale_log2, -m2));
+            if (kDrop && !drop_keep(drop, rowe + (unsigned long long)(Nk + t))) pt = 0.f;
+            const __nv_bfloat16* vrow = qkv + ((long long)b * N + Nk + t) * (3LL * D) + 2 * D + h * kHd + hf * 32;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vrow + 8 * c));
+              const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[i]));
+                o[8 * c + 2 * i] = __float_as_uint(fmaf(pt, f.x, __uint_as_float(o[8 * c + 2 * i])));
+                o[8 * c + 2 * i + 1] = __float_as_uint(fmaf(pt, f.y, __uint_as_float(o[8 * c + 2 * i + 1])));
+              }
+            }
+          }
+      }
       if (q < N) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {  // 16 bf16 = one full 32-byte sector per store (D % 16 == 0)
@@ -293,10 +372,12 @@ int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int
   dim3 grid((N + kTile - 1) / kTile, H, B);
   const float scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
   const DropCfg dc = make_drop(drop);
+  const int tail = attn_tail(N);
+  const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv;
   if (dc.thr16 != 0)
-    tc_attn_fwd_kernel<true><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, scale_log2, dc);
+    tc_attn_fwd_kernel<true><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, qp, (__nv_bfloat16*)out, lse, N, tail, H, scale_log2, dc);
   else
-    tc_attn_fwd_kernel<false><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, scale_log2, dc);
+    tc_attn_fwd_kernel<false><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, qp, (__nv_bfloat16*)out, lse, N, tail, H, scale_log2, dc);
   TVIT_LAUNCH_OK();
   return TVIT_OK;
 }

@@ -21,6 +21,12 @@
 // b of tile i.  Q/dO tiles are triple-buffered, dS double-buffered, P single-buffered (dV_i is issued first and
 // frees it long before the first P store of tile i+1).  Each CTA starts its query loop at its own key-tile index
 // (i -> (i + j) mod nq) so that the CTAs of one (sample, head) never reduce into the same dQ tile at once.
+//
+// Ragged tail: when N = 128 m + t with a small t (N = 2049 = 16 * 128 + 1 at the bench shape), the last t QUERIES are
+// not given a query tile of their own (one more trip through the five-MMA loop for one valid row: 1/17 of the kernel).
+// Every key-tile CTA handles them in its epilogue on the CUDA cores, thread == key row with K_j / V_j still in shared
+// memory: s = q_t . k, dP = dO_t . v, dS as in the loop; dK_j / dV_j get the rank-1 updates before they are stored and
+// the partial dQ_t = sum_k dS k is warp-reduced and added to the same fp32 accumulator the drained dQ tiles go to.
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -33,6 +39,23 @@ constexpr int kTileBytesB = kTileB * kHdB * 2;  // 16384: one [128 x 64] bf16 op
 constexpr int kPBytes = kTileB * kTileB * 2;    // 32768: one [128 x 128] bf16 P / dS tile (two 64-wide blocks)
 constexpr int kAttnBwdThreads = 768;  // warps 0-15 softmax, 16-19 dQ drain, 20 TMA, 21 MMA (+TMEM alloc), 22-23 idle
 constexpr int kSoftmaxWarps = 16;
+
+__device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b, float acc) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
+    const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[i]));
+    acc = fmaf(fa.x, fb.x, acc);
+    acc = fmaf(fa.y, fb.y, acc);
+  }
+  return acc;
+}
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 
 constexpr int kQStages = 3;  // Q / dO tiles in flight
 struct AttnBwdSmem {
@@ -98,8 +121,9 @@ __global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_
 template <bool kDrop>
 __global__ void __launch_bounds__(kAttnBwdThreads, 1)
 tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ dvec, float* __restrict__ dqacc,
-                   __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale, DropCfg drop) {
+                   __nv_bfloat16* __restrict__ dqkv, int N, int tail, int H, float scale, DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;
@@ -120,7 +144,9 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int D = H * kHdB;
   const int kv0 = jt * kTileB;
-  const int nq = (N + kTileB - 1) / kTileB;
+  const int nqt = (N + kTileB - 1) / kTileB;  // query tiles of the dQ accumulator
+  const int Nq = N - tail;                    // queries that go through the tile loop
+  const int nq = (Nq + kTileB - 1) / kTileB;  // tiles in the loop (== nqt unless there is a tail)
 
   if (threadIdx.x == 0) {
     mbar_init(&sm->kv_full, 1);
@@ -374,6 +400,63 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       uint32_t o[32];
       tmem_ld32(tsrc + lane_off + c * 32, o);
       tmem_ld_wait();
+      for (int t = 0; t < tail; ++t) {  // ---- tail queries (see header): thread == key row kv ----
+        const int qi = Nq + t;
+        const __nv_bfloat16* qrow = qkv + ((long long)b * N + qi) * (3LL * D) + h * kHdB;
+        const __nv_bfloat16* dorow = dout + ((long long)b * N + qi) * D + h * kHdB;
+        const uint32_t krow = smem_u32(sK) + (uint32_t)r * 128u, vrow = smem_u32(sV) + (uint32_t)r * 128u;
+        float sc = 0.f, dpv = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {  // 16-byte pieces of the 128B-swizzled K / V rows
+          const uint32_t sw = (uint32_t)((cc ^ (r & 7)) * 16);
+          sc = dot8_bf16(ld_shared_u4(krow + sw), __ldg(reinterpret_cast<const uint4*>(qrow + 8 * cc)), sc);
+          dpv = dot8_bf16(ld_shared_u4(vrow + sw), __ldg(reinterpret_cast<const uint4*>(dorow + 8 * cc)), dpv);
+        }
+        float pt = ex2_approx(fmaf(sc, c_log2, -lse_bh[qi] * 1.4426950408889634f));
+        float mlt = 1.0f;
+        if (kDrop) mlt = drop_keep(drop, attn_drop_row_base(b, H, h, N, qi) + (unsigned long long)kv) ? drop.inv_keep : 0.f;
+        float dst = pt * (dpv * mlt - dv_bh[qi]) * scale, pmt = pt * mlt;
+        if (kv >= N) dst = pmt = 0.f;
+        {  // rank-1 updates of this thread's 32 columns: dK += dS q_t, dV += (P mask) dO_t
+          const __nv_bfloat16* src = (which == 0 ? qrow : dorow) + c * 32;
+          const float f = which == 0 ? dst : pmt;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint4 vv = __ldg(reinterpret_cast<const uint4*>(src + 8 * cc));
+            const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[i]));
+              o[8 * cc + 2 * i] = __float_as_uint(fmaf(f, g.x, __uint_as_float(o[8 * cc + 2 * i])));
+              o[8 * cc + 2 * i + 1] = __float_as_uint(fmaf(f, g.y, __uint_as_float(o[8 * cc + 2 * i + 1])));
+            }
+          }
+        }
+        if (chunk == 0) {  // dQ_t += sum over this warp's 32 key rows of dS k: one warp per lane quarter
+          float* trow = dqacc + (((long long)b * H + h) * nqt + nq) * (16LL * 128 * 4) + t * 4;
+#pragma unroll 1
+          for (int cc = 0; cc < 8; ++cc) {
+            const uint4 kk = ld_shared_u4(krow + (uint32_t)((cc ^ (r & 7)) * 16));
+            const uint32_t kw[4] = {kk.x, kk.y, kk.z, kk.w};
+            float v8[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[i]));
+              v8[2 * i] = dst * g.x;
+              v8[2 * i + 1] = dst * g.y;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v8[i] += __shfl_xor_sync(0xffffffffu, v8[i], off);
+            float val = v8[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) val = (lane == i) ? v8[i] : val;
+            // column d = 8 cc + lane of accumulator row t: chunk d / 4, element d % 4
+            if (lane < 8) atomicAdd(trow + (2 * cc + (lane >> 2)) * 512 + (lane & 3), val);
+          }
+        }
+      }
       if (kv < N) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {  // 16 bf16 = one full 32-byte sector per store
@@ -390,7 +473,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const int qd = warp & 3;  // TMEM lane quarter (warp % 4)
     const int r = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    float* acc_bh = dqacc + ((long long)b * H + h) * nq * (16LL * 128 * 4);
+    float* acc_bh = dqacc + ((long long)b * H + h) * nqt * (16LL * 128 * 4);
     for (int i = 0; i < nq; ++i) {
       mbar_wait_backoff(&sm->dq_full, (uint32_t)i & 1u);
       tc_fence_after();
@@ -468,10 +551,13 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   dim3 grid(nq, H, B);
   const float scale = 1.0f / sqrtf((float)hd);
   const DropCfg dc = make_drop(drop);
+  const int tail = attn_tail(N);
+  const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv;
+  const __nv_bfloat16* dop = (const __nv_bfloat16*)dout;
   if (dc.thr16 != 0)
-    tc_attn_bwd_kernel<true><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, N, H, scale, dc);
+    tc_attn_bwd_kernel<true><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, qp, dop, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, N, tail, H, scale, dc);
   else
-    tc_attn_bwd_kernel<false><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, N, H, scale, dc);
+    tc_attn_bwd_kernel<false><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, qp, dop, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, N, tail, H, scale, dc);
   TVIT_LAUNCH_OK();
   {
     const long long total = (long long)B * H * nq * 4 * 128;

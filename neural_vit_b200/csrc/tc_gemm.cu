@@ -363,11 +363,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // global epilogue operands are double-buffered in registers: chunk u+1 is requested before chunk u is
       // processed (and the first chunk before the accumulator is even complete), so every thread keeps two chunks
       // of loads in flight
-      uint32_t ext[2][16];
       constexpr bool kExt = (EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_GELU_BWD);
       constexpr int kHalfSub = BN / 16 / kGroups;
-      if (kExt && ep.vec16_ok && n0 + half * kHalfSub * 16 + 16 <= sh.N)
-        tc_epi16_load<EPI>(ep, m, n0 + half * kHalfSub * 16, row_ok, ext[0]);
+      // GELU_BWD reads 8 words per chunk: ALL chunks of the tile are requested up front (32 registers), before the
+      // accumulator is even complete, so their global-load latency overlaps the main loop instead of stalling every
+      // chunk (ncu: 12.5 long-scoreboard stalls per issue with the one-chunk-ahead scheme).  RESIDUAL needs 16 words
+      // per chunk and keeps the two-deep register ring.
+      constexpr bool kAllUpfront = (EPI == TVIT_EPI_GELU_BWD) && kHalfSub <= 4;
+      constexpr int kBuf = kAllUpfront ? kHalfSub : 2;
+      uint32_t ext[kBuf][16];
+      if (kExt && ep.vec16_ok) {
+        if (kAllUpfront) {
+#pragma unroll
+          for (int uu = 0; uu < kHalfSub; ++uu) {
+            const int nc = n0 + (half * kHalfSub + uu) * 16;
+            if (nc + 16 <= sh.N) tc_epi16_load<EPI>(ep, m, nc, row_ok, ext[uu]);
+          }
+        } else if (n0 + half * kHalfSub * 16 + 16 <= sh.N) {
+          tc_epi16_load<EPI>(ep, m, n0 + half * kHalfSub * 16, row_ok, ext[0]);
+        }
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -383,10 +398,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (nc >= sh.N) break;  // warp-uniform (N % 16 == 0 on this path is implied by vec8_ok only for N % 8;
                                   // a trailing 8-column piece falls to the generic path below)
           if (nc + 16 <= sh.N) {
-            if (kExt && uu + 1 < kHalfSub && nc + 32 <= sh.N) tc_epi16_load<EPI>(ep, m, nc + 16, row_ok, ext[(uu + 1) & 1]);
+            if (kExt && !kAllUpfront && uu + 1 < kHalfSub && nc + 32 <= sh.N)
+              tc_epi16_load<EPI>(ep, m, nc + 16, row_ok, ext[(uu + 1) % kBuf]);
             const uint32_t so = sb_addr + (uint32_t)(uu * 64);
             tc_epi16<EPI, kDrop>(ep, so, so + (uint32_t)(kW * 4), rsc, m, nc, taddr + (uint32_t)(u * 16), row_ok,
-                                 ext[uu & 1]);
+                                 ext[uu % kBuf]);
           } else {
             uint32_t r[16];
             tmem_ld16(taddr + (uint32_t)(u * 16), r);
