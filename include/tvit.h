@@ -112,6 +112,8 @@ typedef struct {
   int Kp, Fp, Tp;
   int split_k; /* ACCUM_F32: number of K splits, 0 = choose */
   float alpha; /* SOFTMAX_PROBS: score scale (head_dim^-0.5) */
+  float* colsum; /* GELU_BWD, optional: colsum[n] += sum_m out[m,n] (fp32, before rounding): the bias gradient of the
+                    Linear whose pre-activation gradient this GEMM produces, folded into the epilogue. Caller zero-fills. */
 } tvit_gemm_args;
 
 int tvit_gemm(const tvit_gemm_args* args, tvit_stream_t stream);
@@ -127,10 +129,12 @@ int tvit_gemm(const tvit_gemm_args* args, tvit_stream_t stream);
 int tvit_attn_fwd(int engine, int dtype, const void* qkv, void* out, float* lse, int B, int N, int H, int hd,
                   const tvit_dropout* drop, tvit_stream_t stream);
 size_t tvit_attn_bwd_workspace_bytes(int engine, int dtype, int B, int N, int H, int hd);
-/* dqkv : [B*N, 3*H*hd] act.  workspace must hold tvit_attn_bwd_workspace_bytes() bytes. */
+/* dqkv : [B*N, 3*H*hd] act.  workspace must hold tvit_attn_bwd_workspace_bytes() bytes.
+ * dqkv_colsum (optional, fp32 [3*H*hd], caller zero-fills): += column sums of dqkv taken in fp32 before rounding --
+ * the gradient of the qkv bias (model.py:101), folded into the kernels that produce dqkv. */
 int tvit_attn_bwd(int engine, int dtype, const void* qkv, const void* out, const void* dout, const float* lse,
                   void* dqkv, void* workspace, size_t workspace_bytes, int B, int N, int H, int hd,
-                  const tvit_dropout* drop, tvit_stream_t stream);
+                  const tvit_dropout* drop, float* dqkv_colsum, tvit_stream_t stream);
 /* probs[b,h,q,k] = softmax(q k^T * hd^-0.5) materialised (interpretability API, model.py:325-350) */
 int tvit_attn_probs(int dtype, const void* qkv, float* probs, int B, int N, int H, int hd, tvit_stream_t stream);
 

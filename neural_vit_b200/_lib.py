@@ -36,6 +36,7 @@ class GemmArgs(ctypes.Structure):
         ("rows_per_group", c_int), ("drop", Dropout),
         ("pos_k", c_void_p), ("pos_f", c_void_p), ("pos_t", c_void_p),
         ("Kp", c_int), ("Fp", c_int), ("Tp", c_int), ("split_k", c_int), ("alpha", c_float),
+        ("colsum", c_void_p),
     ]
 
 
@@ -55,7 +56,7 @@ SIGNATURES = {
                               ctypes.POINTER(Dropout), c_void_p]),
     "tvit_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "tvit_attn_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                              c_int, c_int, c_int, c_int, ctypes.POINTER(Dropout), c_void_p]),
+                              c_int, c_int, c_int, c_int, ctypes.POINTER(Dropout), c_void_p, c_void_p]),
     "tvit_attn_probs": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tvit_im2col": (c_int, [c_void_p, c_void_p, c_int] + [c_int] * 7 + [c_void_p]),
     "tvit_ln_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int,

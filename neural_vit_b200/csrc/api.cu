@@ -44,7 +44,8 @@ int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int
                 cudaStream_t s);
 size_t tc_attn_bwd_workspace(int B, int N, int H, int hd);
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* ws,
-                size_t ws_bytes, int B, int N, int H, int hd, const tvit_dropout* drop, cudaStream_t s);
+                size_t ws_bytes, int B, int N, int H, int hd, const tvit_dropout* drop, float* dqkv_colsum,
+                cudaStream_t s);
 
 }  // namespace tvit
 
@@ -117,15 +118,18 @@ extern "C" size_t tvit_attn_bwd_workspace_bytes(int engine, int dtype, int B, in
 
 extern "C" int tvit_attn_bwd(int engine, int dtype, const void* qkv, const void* out, const void* dout,
                              const float* lse, void* dqkv, void* workspace, size_t workspace_bytes, int B, int N, int H,
-                             int hd, const tvit_dropout* drop, tvit_stream_t stream) {
+                             int hd, const tvit_dropout* drop, float* dqkv_colsum, tvit_stream_t stream) {
   TVIT_CHECK_ARG(qkv && out && dout && lse && dqkv, "attn_bwd: null pointer");
   TVIT_CHECK_ARG(B > 0 && N > 0 && H > 0 && hd > 0, "attn_bwd: bad shape");
   cudaStream_t s = (cudaStream_t)stream;
-  if (engine == TVIT_ENGINE_SIMT)
-    return simt_attn_bwd(dtype, qkv, out, dout, lse, dqkv, workspace, workspace_bytes, B, N, H, hd, drop, s);
+  if (engine == TVIT_ENGINE_SIMT) {
+    int rc = simt_attn_bwd(dtype, qkv, out, dout, lse, dqkv, workspace, workspace_bytes, B, N, H, hd, drop, s);
+    if (rc != TVIT_OK || !dqkv_colsum) return rc;
+    return tvit_colsum(dqkv, dtype, (long long)B * N, 3 * H * hd, 3LL * H * hd, dqkv_colsum, stream);
+  }
   if (engine == TVIT_ENGINE_TCGEN05) {
     TVIT_CHECK_ARG(dtype == TVIT_BF16, "attn_bwd: tcgen05 engine needs bf16");
-    return tc_attn_bwd(qkv, out, dout, lse, dqkv, workspace, workspace_bytes, B, N, H, hd, drop, s);
+    return tc_attn_bwd(qkv, out, dout, lse, dqkv, workspace, workspace_bytes, B, N, H, hd, drop, dqkv_colsum, s);
   }
   return fail(TVIT_ERR_BAD_ARG, "attn_bwd: unknown engine %d", engine);
 }

@@ -23,6 +23,7 @@ struct EpiParams {
   const float* pos_t;
   int Kp, Fp, Tp;
   float alpha;  // SOFTMAX_PROBS score scale
+  float* colsum;  // GELU_BWD: optional column sums of the output (bias gradient)
   int vec_ok;   // N % 4 == 0 and every leading dimension % 4 == 0 -> 4-wide vector path is legal
   int vec8_ok;  // same with 8 (16-byte bf16 accesses)
   int vec16_ok; // N, leading dimensions % 16 == 0 and 32-byte aligned bases: 256-bit (full-sector) accesses
@@ -50,6 +51,7 @@ inline EpiParams make_epi_params(const tvit_gemm_args* a) {
   p.Fp = a->Fp;
   p.Tp = a->Tp;
   p.alpha = a->alpha;
+  p.colsum = a->colsum;
   p.vec_ok = (a->N % 4 == 0) && (a->ldo % 4 == 0) && (a->aux == nullptr || a->ldaux % 4 == 0) &&
              (a->resid == nullptr || a->ldres % 4 == 0);
   p.vec8_ok = (a->N % 8 == 0) && (a->ldo % 8 == 0) && (a->aux == nullptr || a->ldaux % 8 == 0);
@@ -108,7 +110,9 @@ __device__ __forceinline__ void epi_apply1(const EpiParams& p, int m, int n, flo
     if (p.row_scale) v *= p.row_scale[m / p.rpg];
     ((float*)p.out)[m * p.ldo + n] = p.resid[m * p.ldres + n] + v;
   } else if (EPI == TVIT_EPI_GELU_BWD) {
-    Act<T>::st((T*)p.out + m * p.ldo + n, v * Act<T>::ld((const T*)p.aux + m * p.ldaux + n));
+    const float o = v * Act<T>::ld((const T*)p.aux + m * p.ldaux + n);
+    Act<T>::st((T*)p.out + m * p.ldo + n, o);
+    if (p.colsum) atomicAdd(p.colsum + n, o);  // generic path only; the tcgen05 fast path reduces per warp first
   } else if (EPI == TVIT_EPI_ACCUM_F32) {
     atomicAdd((float*)p.out + m * p.ldo + n, v);
   } else if (EPI == TVIT_EPI_SOFTMAX_PROBS) {
@@ -168,7 +172,12 @@ __device__ __forceinline__ void epi_apply4(const EpiParams& p, int m, int n0, fl
                     r.w + rs * g.w * v.w * mlt[3]));
   } else if (EPI == TVIT_EPI_GELU_BWD) {
     const float4 h = ld4((const T*)p.aux + m * p.ldaux + n0);
-    st4((T*)p.out + m * p.ldo + n0, make_float4(v.x * h.x, v.y * h.y, v.z * h.z, v.w * h.w));
+    const float4 o = make_float4(v.x * h.x, v.y * h.y, v.z * h.z, v.w * h.w);
+    st4((T*)p.out + m * p.ldo + n0, o);
+    if (p.colsum) {
+      atomicAdd(p.colsum + n0, o.x); atomicAdd(p.colsum + n0 + 1, o.y);
+      atomicAdd(p.colsum + n0 + 2, o.z); atomicAdd(p.colsum + n0 + 3, o.w);
+    }
   } else if (EPI == TVIT_EPI_ACCUM_F32) {
     float* o = (float*)p.out + m * p.ldo + n0;
     atomicAdd(o + 0, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
@@ -202,7 +211,7 @@ template <int EPI, typename T>
 __device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, const float (&v)[8]) {
   constexpr bool kWide = (sizeof(T) == 2) &&
                          (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_GELU_BWD);
-  if (kWide && p.vec8_ok && n0 + 8 <= p.N) {
+  if (kWide && p.vec8_ok && n0 + 8 <= p.N && !(EPI == TVIT_EPI_GELU_BWD && p.colsum)) {
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = v[j];
@@ -292,9 +301,25 @@ __device__ __forceinline__ void tc_epi16_load(const EpiParams& p, int m, int nc,
   }
 }
 
+// Sum 16 per-thread values over the 32 lanes of the warp with a halving butterfly (62 instructions instead of 16 x 5
+// shuffle-adds): afterwards the EVEN lane L holds the total of value index L >> 1 in v[0].
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1) {  // exchange partner: lane ^ (2 w); keeps w values
+    const bool hi = (lane & (2 * w)) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = hi ? v[i] : v[i + w], keep = hi ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 template <int EPI, bool kDrop>
 __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, uint32_t s_gamma, float row_scale, int m,
-                                         int nc, uint32_t taddr, bool row_ok, const uint32_t (&ext)[16]) {
+                                         int nc, uint32_t taddr, bool row_ok, const uint32_t (&ext)[16],
+                                         float (&colv)[16]) {
   constexpr bool kBias = (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL);
   uint32_t acc[16];
   asm volatile(
@@ -315,6 +340,10 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
     for (int j = 0; j < 4; ++j) g[j] = ld_shared_f4(s_gamma + 16 * j);
   }
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (EPI == TVIT_EPI_GELU_BWD) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) colv[j] = 0.f;  // rows past M contribute nothing to the column sums
+  }
   if (!row_ok) return;
 
   // All arithmetic below is packed fp32x2 (FFMA2 / FMUL2 / FADD2: two fp32 results per issue slot, bit-identical per
@@ -377,6 +406,8 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
       float o0, o1;
       up2(mul2(x[j], pk2(f.x, f.y)), o0, o1);
       v[j] = pack_bf16(o0, o1);
+      colv[2 * j] = o0;
+      colv[2 * j + 1] = o1;
     }
     st_global_v8((__nv_bfloat16*)p.out + m * p.ldo + nc, v);
     return;

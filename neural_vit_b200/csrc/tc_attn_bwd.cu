@@ -57,6 +57,33 @@ __device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
   return v;
 }
 
+// Column sums over the 32 lanes of a warp with halving butterflies: lane L ends up with the total of v[L] (32 values)
+// resp. the even lane L with the total of v[L >> 1] (16 values).
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool hi = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = hi ? v[i] : v[i + w], keep = hi ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1) {
+    const bool hi = (lane & (2 * w)) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = hi ? v[i] : v[i + w], keep = hi ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 constexpr int kQStages = 3;  // Q / dO tiles in flight
 struct AttnBwdSmem {
   uint64_t kv_full, qdo_full[kQStages], qdo_empty[kQStages], s_full[2], s_free[2], p_full, p_free, ds_free[2], dq_full,
@@ -93,10 +120,10 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const 
 
 // dq accumulator layout: [(b*H+h)][q tile][16 chunks][128 rows][4 fp32]
 // thread = (row r, group of 4 chunks): four coalesced float4 reads, one full-sector 32-byte bf16 store
-__global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_bfloat16* __restrict__ dqkv, int B,
-                                          int N, int H, int nq) {
+__global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_bfloat16* __restrict__ dqkv,
+                                          float* __restrict__ colsum, int B, int N, int H, int nq) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long total = (long long)B * H * nq * 4 * 128;
+  const long long total = (long long)B * H * nq * 4 * 128;  // a multiple of the block size: whole blocks drop out
   if (idx >= total) return;
   const int r = (int)(idx & 127);
   const int cg = (int)((idx >> 7) & 3);
@@ -105,17 +132,28 @@ __global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_
   const long long bh = t / nq;
   const int h = (int)(bh % H), b = (int)(bh / H);
   const int q = i * kTileB + r;
-  if (q >= N) return;
   const float* src = dqacc + ((t * 16 + 4 * cg) * 128 + r) * 4;
-  uint32_t v[8];
+  float f[16];
+  if (q < N) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float4 f = *reinterpret_cast<const float4*>(src + (long long)k * 512);
-    v[2 * k] = pack_bf16(f.x, f.y);
-    v[2 * k + 1] = pack_bf16(f.z, f.w);
+    for (int k = 0; k < 4; ++k) {
+      const float4 x = *reinterpret_cast<const float4*>(src + (long long)k * 512);
+      f[4 * k] = x.x; f[4 * k + 1] = x.y; f[4 * k + 2] = x.z; f[4 * k + 3] = x.w;
+    }
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = pack_bf16(f[2 * k], f[2 * k + 1]);
+    st_global_b32x8(dqkv + ((long long)b * N + q) * (3LL * H * kHdB) + h * kHdB + 16 * cg, v[0], v[1], v[2], v[3], v[4],
+                    v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = 0.f;
   }
-  st_global_b32x8(dqkv + ((long long)b * N + q) * (3LL * H * kHdB) + h * kHdB + 16 * cg, v[0], v[1], v[2], v[3], v[4],
-                  v[5], v[6], v[7]);
+  if (colsum) {  // dq part of the qkv-bias gradient: a warp holds 32 rows of the same 16 columns
+    const int lane = threadIdx.x & 31;
+    const float tot = warp_colsum16(f, lane);
+    if ((lane & 1) == 0) atomicAdd(colsum + h * kHdB + 16 * cg + (lane >> 1), tot);
+  }
 }
 
 template <bool kDrop>
@@ -123,7 +161,8 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1)
 tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ dvec, float* __restrict__ dqacc,
-                   __nv_bfloat16* __restrict__ dqkv, int N, int tail, int H, float scale, DropCfg drop) {
+                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int N, int tail, int H, float scale,
+                   DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;
@@ -467,6 +506,13 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           st_global_b32x8(drow + (which + 1) * D + c * 32 + 16 * t, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
         }
       }
+      if (colsum) {  // dk / dv parts of the qkv-bias gradient: this warp's 32 key rows x 32 columns (once per CTA)
+        float cv[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) cv[u] = kv < N ? __uint_as_float(o[u]) : 0.f;
+        const float tot = warp_colsum32(cv, lane);
+        atomicAdd(colsum + (which + 1) * D + h * kHdB + c * 32 + lane, tot);
+      }
     }
   } else if (warp < 20) {
     // ============================ dQ drain warps (16-19) ============================
@@ -522,7 +568,8 @@ size_t tc_attn_bwd_workspace(int B, int N, int H, int hd) {
 }
 
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* ws,
-                size_t ws_bytes, int B, int N, int H, int hd, const tvit_dropout* drop, cudaStream_t s) {
+                size_t ws_bytes, int B, int N, int H, int hd, const tvit_dropout* drop, float* dqkv_colsum,
+                cudaStream_t s) {
   if (hd != kHdB) return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 attention supports head_dim 64 only (got %d)", hd);
   if (!ws || ws_bytes < tc_attn_bwd_workspace(B, N, H, hd))
     return fail(TVIT_ERR_BAD_ARG, "attn_bwd: workspace too small (%zu < %zu)", ws_bytes,
@@ -555,13 +602,14 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv;
   const __nv_bfloat16* dop = (const __nv_bfloat16*)dout;
   if (dc.thr16 != 0)
-    tc_attn_bwd_kernel<true><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, qp, dop, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, N, tail, H, scale, dc);
+    tc_attn_bwd_kernel<true><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, qp, dop, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, N, tail, H, scale, dc);
   else
-    tc_attn_bwd_kernel<false><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, qp, dop, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, N, tail, H, scale, dc);
+    tc_attn_bwd_kernel<false><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, qp, dop, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, N, tail, H, scale, dc);
   TVIT_LAUNCH_OK();
   {
     const long long total = (long long)B * H * nq * 4 * 128;
-    attn_bwd_dq_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dqacc, (__nv_bfloat16*)dqkv, B, N, H, nq);
+    attn_bwd_dq_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, B,
+                                                                              N, H, nq);
     TVIT_LAUNCH_OK();
   }
   return TVIT_OK;

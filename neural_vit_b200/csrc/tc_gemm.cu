@@ -329,10 +329,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 4) >> 2;  // column group of this warp
     constexpr int kGroups = EpiCfg<BN>::kGroups;
     constexpr int kChunks = BN / 32, kHalfChunks = kChunks / kGroups;
+    // GELU_BWD with ep.colsum: per-column sums of the output (the bias gradient of the preceding Linear) are
+    // accumulated in this warp's private smem slice across tiles (it is not needed for bias / gamma staging in this
+    // epilogue) and flushed with one atomic per column when the n-tile changes -- with the weight-stationary
+    // schedule (B_RES) that is once per CTA.
+    constexpr int kWc = BN / kGroups;
+    const bool do_colsum = (EPI == TVIT_EPI_GELU_BWD) && ep.colsum != nullptr && ep.vec16_ok;
+    float* cs_slice = s_cols + (warp - 4) * (2 * kWc);
+    int cs_n0 = -1;
+    auto flush_colsum = [&]() {
+      if (cs_n0 < 0) return;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kWc / 32; ++j) {
+        const int e = j * 32 + lane, col = cs_n0 + half * kWc + e;
+        if (col < sh.N) atomicAdd(ep.colsum + col, cs_slice[e]);
+        cs_slice[e] = 0.f;
+      }
+      __syncwarp();
+    };
+    if (do_colsum) {
+#pragma unroll
+      for (int j = 0; j < kWc / 32; ++j) cs_slice[j * 32 + lane] = 0.f;
+      __syncwarp();
+    }
     int it = 0;
     for (int w = w_first; w < total_work; w += w_step, ++it) {
       const int tile = w / sh.splits;
       const int m0 = (tile / sh.n_tiles) * kBM, n0 = (tile % sh.n_tiles) * BN;
+      if (do_colsum && n0 != cs_n0) {
+        flush_colsum();
+        cs_n0 = n0;
+      }
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       // GELU_BWD: request the NEXT tile's bf16 pre-activations (this thread's row segment) into L2 now, one epilogue
@@ -348,7 +376,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // shared memory: only __syncwarp is needed, so the epilogue warps never wait for each other.
       constexpr int kW = BN / kGroups;  // columns per warp
       float* sb = s_cols + (warp - 4) * (2 * kW);
-      {
+      if (EPI != TVIT_EPI_GELU_BWD) {  // (GELU_BWD reads neither; its slice holds the column sums)
         __syncwarp();  // the previous tile's reads of this slice are done
 #pragma unroll
         for (int j = 0; j < kW / 32; ++j) {
@@ -401,8 +429,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (kExt && !kAllUpfront && uu + 1 < kHalfSub && nc + 32 <= sh.N)
               tc_epi16_load<EPI>(ep, m, nc + 16, row_ok, ext[(uu + 1) % kBuf]);
             const uint32_t so = sb_addr + (uint32_t)(uu * 64);
+            float colv[16];
             tc_epi16<EPI, kDrop>(ep, so, so + (uint32_t)(kW * 4), rsc, m, nc, taddr + (uint32_t)(u * 16), row_ok,
-                                 ext[uu % kBuf]);
+                                 ext[uu % kBuf], colv);
+            if (do_colsum) {  // warp-uniform
+              const float tot = warp_colsum16(colv, lane);
+              if ((lane & 1) == 0) cs_slice[uu * 16 + (lane >> 1)] += tot;
+            }
           } else {
             uint32_t r[16];
             tmem_ld16(taddr + (uint32_t)(u * 16), r);
@@ -437,6 +470,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
+    if (do_colsum) flush_colsum();
   }
 
   tc_fence_before();

@@ -333,7 +333,8 @@ class _BlockFn(torch.autograd.Function):
             cs2, _ = _dst(sk, I_F2B, (D,), dev)            # without LayerScale colsum(gp) IS the bias gradient
         ops.branch_grad_prep(g_out, M, D, s2, N, d_fc2, gp2, T, cs2)
         dh = _empty((M, hid), td, dev)   # grad wrt fc1 pre-activation
-        ops.gemm(E, T, gp2, fc2_wt, M, hid, D, epilogue=L.EPI_GELU_BWD, out=dh, aux=hpre)
+        d_f1b, _ = _dst(sk, I_F1B, (hid,), dev)     # = colsum(dh): folded into the epilogue of the GEMM producing dh
+        ops.gemm(E, T, gp2, fc2_wt, M, hid, D, epilogue=L.EPI_GELU_BWD, out=dh, aux=hpre, colsum=d_f1b)
         if ctx.has_ls:
             G2 = _zeros((D, hid), dev)
         else:
@@ -347,8 +348,6 @@ class _BlockFn(torch.autograd.Function):
             ops.ls_finalize(G2, f2w, g2, f2b, cs2, d_f2w, d_g2, d_f2b, D, hid, accumulate=use)
         else:
             d_f2w, d_g2, d_f2b = G2, None, cs2
-        d_f1b, _ = _dst(sk, I_F1B, (hid,), dev)
-        ops.colsum(dh, T, M, hid, hid, d_f1b)
         d_f1w, _ = _dst(sk, I_F1W, (hid, D), dev)
         ops.gemm(E, T, dh, y2, hid, D, M, epilogue=L.EPI_ACCUM_F32, out=d_f1w, trans_a=True, trans_b=True)
         dy2 = _empty((M, D), td, dev)
@@ -383,9 +382,8 @@ class _BlockFn(torch.autograd.Function):
         else:
             d_pw, d_g1, d_pb = Gp, None, cs1
         dqkv = _empty((M, 3 * D), td, dev)
-        ops.attn_bwd(rt.attn_engine, T, qkv, ao, dao, lse, dqkv, B, N, H, hd, d_attn)
-        d_qkvb, _ = _dst(sk, I_QKVB, (3 * D,), dev)
-        ops.colsum(dqkv, T, M, 3 * D, 3 * D, d_qkvb)
+        d_qkvb, _ = _dst(sk, I_QKVB, (3 * D,), dev)   # = colsum(dqkv): folded into the attention-backward kernels
+        ops.attn_bwd(rt.attn_engine, T, qkv, ao, dao, lse, dqkv, B, N, H, hd, d_attn, colsum=d_qkvb)
         d_qkvw, _ = _dst(sk, I_QKVW, (3 * D, D), dev)
         ops.gemm(E, T, dqkv, y1, 3 * D, D, M, epilogue=L.EPI_ACCUM_F32, out=d_qkvw, trans_a=True, trans_b=True)
         dy1 = _empty((M, D), td, dev)

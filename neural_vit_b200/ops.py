@@ -92,7 +92,7 @@ def gemm(engine: int, dtype: int, a: torch.Tensor, b: torch.Tensor, M: int, N: i
          trans_a: bool = False, trans_b: bool = False, bias=None, aux=None, resid=None, gamma=None, row_scale=None,
          rows_per_group: int = 0, drop: DropSpec = None, pos=None, grid3=None, split_k: int = 0,
          alpha: float = 1.0, a_offset: int = 0, b_offset: int = 0, out_offset: int = 0,
-         row_scale_offset: int = 0) -> None:
+         row_scale_offset: int = 0, colsum=None) -> None:
     """C[M,N] = op(A) op(B)^T with a fused epilogue (see tvit_gemm in include/tvit.h)."""
     td = torch_dtype(dtype)
     _req(a, td, "gemm A")
@@ -118,6 +118,7 @@ def gemm(engine: int, dtype: int, a: torch.Tensor, b: torch.Tensor, M: int, N: i
         args.Kp, args.Fp, args.Tp = grid3
     args.split_k = split_k
     args.alpha = alpha
+    args.colsum = _ptr(colsum)
     _count("gemm")
     with _timed(("gemm_e%d%s" % (epilogue, "_tn" if trans_a else "")) if TIMED is None or "detail" not in TIMED
                 else "gemm_e%d%s_N%d_K%d" % (epilogue, "_tn" if trans_a else "", N, K)):
@@ -145,14 +146,15 @@ def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     return ws
 
 
-def attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, B, N, H, hd, drop: DropSpec = None) -> None:
+def attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, B, N, H, hd, drop: DropSpec = None, colsum=None) -> None:
     lib = L.load()
     nbytes = int(lib.tvit_attn_bwd_workspace_bytes(engine, dtype, B, N, H, hd))
     ws = workspace(nbytes, qkv.device)
     _count("attn_bwd" if engine == L.ENGINE_TCGEN05 else "attn_bwd_simt")
     with _timed("attn_bwd"):
         L.check(lib.tvit_attn_bwd(engine, dtype, qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-                                  dqkv.data_ptr(), ws.data_ptr(), nbytes, B, N, H, hd, _drop_ptr(drop), _stream()),
+                                  dqkv.data_ptr(), ws.data_ptr(), nbytes, B, N, H, hd, _drop_ptr(drop), _ptr(colsum),
+                                  _stream()),
                 "tvit_attn_bwd")
 
 

@@ -114,6 +114,16 @@ def test_gemm_gelu_bwd(engine, dtype, tag):
     ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_GELU_BWD, out=out, aux=daux)
     ref = (a.double() @ b.double().T) * daux.double()
     assert rel_err(out, ref) < _tol(dtype)
+    # optional fused column sums of the output (the bias gradient of the preceding Linear); accumulate semantics
+    for (M2, N2) in ((M, N), (40000, 1536), (300, 200)):
+        a2, d2 = _rand((M2, K), dtype, 17), _rand((M2, N2), dtype, 18)
+        b2 = _rand((N2, K), dtype, 19, 1 / math.sqrt(K))
+        out2 = torch.empty((M2, N2), dtype=ops.torch_dtype(dtype), device=DEV)
+        cs = torch.ones(N2, device=DEV)
+        ops.gemm(engine, dtype, a2, b2, M2, N2, K, epilogue=L.EPI_GELU_BWD, out=out2, aux=d2, colsum=cs)
+        ref2 = (a2.double() @ b2.double().T) * d2.double()
+        assert rel_err(out2, ref2) < _tol(dtype)
+        assert rel_err(cs - 1.0, ref2.sum(0)) < (1e-4 if dtype == L.F32 else 2e-3), (M2, N2)
 
 
 @pytest.mark.parametrize("engine,dtype,tag", ENGINES, ids=[e[2] for e in ENGINES])
@@ -264,12 +274,18 @@ def test_attention_fwd_bwd(engine, dtype, tag, Bsz, N, H, hd):
     dout = _rand((Bsz * N, D), dtype, 61)
     ref.backward(dout.double())
     dqkv = torch.empty_like(qkv)
-    ops.attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, Bsz, N, H, hd)
+    cs = torch.zeros(3 * D, device=DEV)
+    ops.attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, Bsz, N, H, hd, colsum=cs)
     tol = 5e-5 if dtype == L.F32 else 2e-2
     g = qd.grad.reshape(Bsz * N, 3, D)
     got = dqkv.reshape(Bsz * N, 3, D)
     for i, nm in enumerate("qkv"):
         assert rel_err(got[:, i], g[:, i]) < tol, f"d{nm}"
+    # fused qkv-bias gradient = column sums of dqkv; the K third is zero in exact arithmetic (softmax shift invariance)
+    want = qd.grad.sum(0)
+    for i in (0, 2):
+        assert rel_err(cs[i * D:(i + 1) * D], want[i * D:(i + 1) * D]) < (1e-4 if dtype == L.F32 else 1e-2), "qkv"[i]
+    assert cs[D:2 * D].abs().max().item() < 1e-2 * cs.abs().max().item() + 1e-6
 
 
 @pytest.mark.parametrize("Bsz,N,H", [(2, 300, 2), (1, 2049, 1), (3, 130, 6), (2, 17, 1)])
