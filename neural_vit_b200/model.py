@@ -333,8 +333,11 @@ class _BlockFn(torch.autograd.Function):
             cs2, _ = _dst(sk, I_F2B, (D,), dev)            # without LayerScale colsum(gp) IS the bias gradient
         ops.branch_grad_prep(g_out, M, D, s2, N, d_fc2, gp2, T, cs2)
         dh = _empty((M, hid), td, dev)   # grad wrt fc1 pre-activation
-        d_f1b, _ = _dst(sk, I_F1B, (hid,), dev)     # = colsum(dh): folded into the epilogue of the GEMM producing dh
-        ops.gemm(E, T, gp2, fc2_wt, M, hid, D, epilogue=L.EPI_GELU_BWD, out=dh, aux=hpre, colsum=d_f1b)
+        ops.gemm(E, T, gp2, fc2_wt, M, hid, D, epilogue=L.EPI_GELU_BWD, out=dh, aux=hpre)
+        # (the GEMM can fold this column sum into its epilogue -- `colsum=` -- but at this shape the warp reductions
+        #  cost the LSU-bound epilogue 0.35 ms against 0.26 ms for the HBM-speed pass below: profiles/r2_kern_v11.log)
+        d_f1b, _ = _dst(sk, I_F1B, (hid,), dev)
+        ops.colsum(dh, T, M, hid, hid, d_f1b)
         if ctx.has_ls:
             G2 = _zeros((D, hid), dev)
         else:
@@ -382,8 +385,13 @@ class _BlockFn(torch.autograd.Function):
         else:
             d_pw, d_g1, d_pb = Gp, None, cs1
         dqkv = _empty((M, 3 * D), td, dev)
-        d_qkvb, _ = _dst(sk, I_QKVB, (3 * D,), dev)   # = colsum(dqkv): folded into the attention-backward kernels
-        ops.attn_bwd(rt.attn_engine, T, qkv, ao, dao, lse, dqkv, B, N, H, hd, d_attn, colsum=d_qkvb)
+        d_qkvb, _ = _dst(sk, I_QKVB, (3 * D,), dev)
+        # colsum(dqkv) (the qkv-bias gradient) is folded into the attention-backward kernels when that is a net win:
+        # with dropout the issue-bound kernel hides it (+0.13 ms vs 0.22 ms for a separate pass), without it does not
+        fuse_cs = d_attn is not None or rt.attn_engine != L.ENGINE_TCGEN05
+        ops.attn_bwd(rt.attn_engine, T, qkv, ao, dao, lse, dqkv, B, N, H, hd, d_attn, colsum=d_qkvb if fuse_cs else None)
+        if not fuse_cs:
+            ops.colsum(dqkv, T, M, 3 * D, 3 * D, d_qkvb)
         d_qkvw, _ = _dst(sk, I_QKVW, (3 * D, D), dev)
         ops.gemm(E, T, dqkv, y1, 3 * D, D, M, epilogue=L.EPI_ACCUM_F32, out=d_qkvw, trans_a=True, trans_b=True)
         dy1 = _empty((M, D), td, dev)

@@ -76,6 +76,9 @@ def main():
         dh = torch.empty(M, hid, dtype=torch.bfloat16, device=DEV)
         ms = timeit(lambda: ops.gemm(E, T, gp, w2t, M, hid, D, epilogue=L.EPI_GELU_BWD, out=dh, aux=aux), a.reps)
         report(f"GELU_BWD dgrad [M,{hid}]x{D}", ms, fl, M * (D * 2 + hid * 4))
+        csf = torch.zeros(hid, device=DEV)
+        ms = timeit(lambda: ops.gemm(E, T, gp, w2t, M, hid, D, epilogue=L.EPI_GELU_BWD, out=dh, aux=aux, colsum=csf), a.reps)
+        report(f"GELU_BWD dgrad + fused colsum", ms, fl, M * (D * 2 + hid * 4))
         ms = timeit(lambda: ops.gemm(E, T, gp, w2t, M, hid, D, epilogue=L.EPI_STORE, out=dh), a.reps)
         report(f"STORE [M,{hid}]x{D} (same shape, plain)", ms, fl, M * (D * 2 + hid * 2))
         w2 = bf(D, hid, scale=1 / math.sqrt(hid))
@@ -117,6 +120,9 @@ def main():
             report(f"attn fwd {tag}", ms, fl)
             ms = timeit(lambda: ops.attn_bwd(E, T, qkv, out, dout, lse, dqkv, B, N, H, hd, d), a.reps)
             report(f"attn bwd {tag} (algorithmic 8 N^2 D)", ms, 2 * fl)
+            csq = torch.zeros(3 * D, device=DEV)
+            ms = timeit(lambda: ops.attn_bwd(E, T, qkv, out, dout, lse, dqkv, B, N, H, hd, d, colsum=csq), a.reps)
+            report(f"attn bwd {tag} + fused qkv-bias colsum", ms, 2 * fl)
         del qkv, out, dout, dqkv
 
     if "elem" in only:
@@ -143,6 +149,10 @@ def main():
         csb = torch.zeros(hid, device=DEV)
         ms = timeit(lambda: ops.colsum(big, T, M, hid, hid, csb), a.reps)
         report(f"colsum [M,{hid}]", ms, None, M * hid * 2)
+        big3 = bf(M, 3 * D)
+        cs3 = torch.zeros(3 * D, device=DEV)
+        ms = timeit(lambda: ops.colsum(big3, T, M, 3 * D, 3 * D, cs3), a.reps)
+        report(f"colsum [M,{3 * D}]", ms, None, M * 3 * D * 2)
 
 
 if __name__ == "__main__":
