@@ -4,6 +4,8 @@
 // CLS / positional-embedding gradients.  (AdamW, multi-tensor shadows and the loss kernel: optim_loss.cu)
 //
 // Each kernel is HBM-bound; the algorithmic bytes per element are listed in DESIGN.md section 4.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tvit {
@@ -104,8 +106,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 // ---------------------------------------------------------------------------------------------
 // LayerNorm backward (+ residual add, + branch-gradient emission, + dgamma/dbeta/colsum partials)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VPL>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, long long xrs,
+// MINB = resident blocks per SM the register allocation is held to: the kernel is latency-bound (ncu: 123 registers ->
+// 2 blocks = 16 warps per SM, 14 long-scoreboard stalls per issue, 4.7 TB/s), so more resident warps can pay for a few
+// spilled accumulators: 4 blocks (64 registers, ~0.4 KB of L1-resident spills) run the plain variant at 5.6 TB/s.
+// TVIT_LN_MINB=2|3 selects the other instantiations for A/B timing.
+template <typename T, int VPL, int MINB>
+__global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, long long xrs,
                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
                                                       const float* __restrict__ w, const float* __restrict__ gres,
                                                       float* __restrict__ dx, long long dxrs, float* __restrict__ dw,
@@ -465,14 +471,24 @@ extern "C" int tvit_ln_bwd(const void* dy, int dtype, const float* x, long long 
   TVIT_CHECK_ARG(!row_scale || rows_per_group > 0, "ln_bwd: rows_per_group must be > 0");
   if (rows == 0) return TVIT_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = blocks_for(rows, 8 * 4, num_sms() * 4);
+  static const int minb = [] {
+    const char* e = getenv("TVIT_LN_MINB");
+    const int v = e ? atoi(e) : 4;  // measured (B200, M = 524544, D = 384): 0.607 / 0.552 / 0.507 ms for 2 / 3 / 4
+    return (v == 2 || v == 3) ? v : 4;
+  }();
+  const int grid = blocks_for(rows, 8 * 4, num_sms() * (minb > 2 ? 2 * minb : 4));
   const DropCfg dc = make_drop(drop);
   const size_t smem = 3 * (size_t)D * sizeof(float);
+#define LN_BWD_LAUNCH(MB)                                                                                            \
+  ln_bwd_kernel<T, VPL, MB><<<grid, 256, smem, s>>>((const T*)dy, x, xrs, mean, rstd, weight, g_res, dx, dxrs, dweight, \
+                                                    dbias, (T*)gp, row_scale, rows_per_group > 0 ? rows_per_group : 1, \
+                                                    dc, gp_colsum, rows, D)
   DISPATCH_T(dtype, DISPATCH_VPL(D, {
-    ln_bwd_kernel<T, VPL><<<grid, 256, smem, s>>>((const T*)dy, x, xrs, mean, rstd, weight, g_res, dx, dxrs, dweight,
-                                                  dbias, (T*)gp, row_scale, rows_per_group > 0 ? rows_per_group : 1,
-                                                  dc, gp_colsum, rows, D);
+    if (minb == 3) LN_BWD_LAUNCH(3);
+    else if (minb == 4) LN_BWD_LAUNCH(4);
+    else LN_BWD_LAUNCH(2);
   }))
+#undef LN_BWD_LAUNCH
   TVIT_LAUNCH_OK();
   return TVIT_OK;
 }
