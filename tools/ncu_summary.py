@@ -1,7 +1,10 @@
 """Summarise an .ncu-rep (run where ncu is installed): per kernel duration, pipe utilisation, stalls, DRAM bytes."""
 import csv, subprocess, sys, json
 rep = sys.argv[1]
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):      # `ncu -i X.ncu-rep --page raw --csv` exported on the GPU box (reports can exceed the 64 MiB pull)
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 want = {
@@ -19,6 +22,9 @@ want = {
     "dram__bytes_write.sum": "dram_wr",
     "smsp__inst_executed.sum": "warp_insts",
     "launch__registers_per_thread": "regs",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "lsu_wavefront_pct",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_pct",
+    "sm__warps_active.avg.pct_of_peak_sustained_active": "occupancy_pct",
 }
 res = []
 for r in rows[2:]:
