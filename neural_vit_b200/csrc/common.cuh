@@ -354,16 +354,19 @@ __device__ __forceinline__ void drop_keep_masks16(const DropCfg& c, unsigned lon
   }
 }
 
-// Ragged tail of the tcgen05 attention kernels: when N = 128 m + t with 1 <= t <= kMaxAttnTail, the last t keys (forward)
-// / queries (backward) are handled on the CUDA cores instead of through an almost empty 128-wide tile.  TVIT_ATTN_TAIL=0
-// in the environment disables it (debugging / A-B timing).
-constexpr int kMaxAttnTail = 4;
-inline int attn_tail(int N) {
-  // measured at the bench shape (r2_kern_v10*.log): with the tail work at the start / end of each CTA its latency is
-  // exposed and cancels the saved tile, so the path is opt-in (TVIT_ATTN_TAIL=1) until it is moved off the critical path
-  static const bool on = [] { const char* e = getenv("TVIT_ATTN_TAIL"); return e && e[0] == '1'; }();
+// Ragged tail of the tcgen05 attention kernels: when N = 128 m + 1 (the CLS token: N = 2049, 16385, ...), the last key
+// (forward) / query (backward) can be handled on the CUDA cores instead of through an almost empty 128-wide tile.
+// Measured at the bench shape (profiles/r2_kern_v13_tail.log): forward -4 % without dropout, -2 % with it (default ON);
+// backward +1.5 ... +2.7 % even with the tail work hidden on the idle dQ-drain warps (default OFF).
+// TVIT_ATTN_TAIL = bit 0: forward, bit 1: backward (A-B timing / debugging).
+constexpr int kMaxAttnTail = 1;
+inline int attn_tail_mask() {
+  static const int m = [] { const char* e = getenv("TVIT_ATTN_TAIL"); return e ? atoi(e) : 1; }();
+  return m;
+}
+inline int attn_tail(int N, int pass_bit) {
   const int t = N % 128;
-  return (on && N > 128 && t >= 1 && t <= kMaxAttnTail) ? t : 0;
+  return ((attn_tail_mask() & pass_bit) && N > 128 && t >= 1 && t <= kMaxAttnTail) ? t : 0;
 }
 
 // Attention-probability dropout (the N x N site) element index: row-major over (b, h, q, k) with the k extent

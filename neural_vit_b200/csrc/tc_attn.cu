@@ -41,10 +41,13 @@ __device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
 }
 
 struct AttnFwdSmem {
-  uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, pv_done;
+  uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, pv_done, tail_full;
   uint32_t tmem_base;
+  uint32_t pad_;
   float xchg[2][2][128];  // [tile parity][key half][row]: partner exchange of row maxima (and final row sums)
+  uint4 tail_kv[16];      // the tail key's K row (pieces 0-7) and V row (pieces 8-15), staged once per CTA
 };
+static_assert(sizeof(AttnFwdSmem) <= 256 + 2048 + 512, "AttnFwdSmem must fit its slot of the dynamic smem block");
 
 template <bool kDrop>
 __global__ void __launch_bounds__(kAttnFwdThreads, 2)
@@ -75,6 +78,7 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
     mbar_init(&sm->s_free, 8);  // one elected arrive per softmax warp
     mbar_init(&sm->p_full, 8);
     mbar_init(&sm->pv_done, 1);
+    mbar_init(&sm->tail_full, 1);
     fence_barrier_init();
   }
   if (warp == 9) {
@@ -96,6 +100,14 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
       tma_load_3d(sQ, &tm_qkv, &sm->q_full, h * kHd, q0, b);
     }
     __syncwarp();
+    if (tail > 0) {  // stage the tail key's K and V rows (2 x 128 B) so that no softmax thread waits on global memory
+      if (lane < 16) {
+        const __nv_bfloat16* row = qkv + ((long long)b * N + Nk) * (3LL * D) + (lane < 8 ? D : 2 * D) + h * kHd;
+        sm->tail_kv[lane] = __ldg(reinterpret_cast<const uint4*>(row + 8 * (lane & 7)));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->tail_full);
+    }
     for (int j = 0; j < nkv; ++j) {
       const int st = j & 1;
       mbar_wait_backoff(&sm->kv_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
@@ -165,36 +177,19 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
     const unsigned long long rowe = attn_drop_row_base(b, H, h, N, q < N ? q : 0);
     // raw scores q . k of the tail keys (both partner threads compute all of them).  They are computed twice -- here
     // and again in the epilogue -- rather than kept in registers across the tile loop (the Q tile stays in smem).
-    auto tail_scores = [&](float (&st)[kMaxAttnTail]) {
+    auto tail_score = [&]() {  // q . k_tail from the Q tile and the staged K row, both in shared memory
+      float st = 0.f;
+      const uint32_t qrow = smem_u32(sQ) + (uint32_t)r * 128u, krow = smem_u32(&sm->tail_kv[0]);
 #pragma unroll
-      for (int t = 0; t < kMaxAttnTail; ++t) st[t] = 0.f;
-      const uint32_t qrow = smem_u32(sQ) + (uint32_t)r * 128u;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {  // 16-byte pieces of the 128B-swizzled row
-        const uint4 qa = ld_shared_u4(qrow + (uint32_t)((c ^ (r & 7)) * 16));
-#pragma unroll
-        for (int t = 0; t < kMaxAttnTail; ++t)
-          if (t < tail) {
-            const uint4 kb = __ldg(reinterpret_cast<const uint4*>(
-                qkv + ((long long)b * N + Nk + t) * (3LL * D) + D + h * kHd + 8 * c));
-            st[t] = dot8_bf16(qa, kb, st[t]);
-          }
-      }
+      for (int c = 0; c < 8; ++c)  // 16-byte pieces of the 128B-swizzled Q row
+        st = dot8_bf16(ld_shared_u4(qrow + (uint32_t)((c ^ (r & 7)) * 16)), ld_shared_u4(krow + 16 * c), st);
+      return st;
     };
-    if (tail > 0) {
-      mbar_wait(&sm->q_full, 0);  // the Q tile has landed (TMA complete_tx)
-      float st[kMaxAttnTail];
-      tail_scores(st);
-      float mt = st[0];
-#pragma unroll
-      for (int t = 1; t < kMaxAttnTail; ++t)
-        if (t < tail) mt = fmaxf(mt, st[t]);
-      m2 = mt * scale_log2;
-      if (hf == 0) {  // the partners' row sums are added at the end: only one of them may count the tail
-#pragma unroll
-        for (int t = 0; t < kMaxAttnTail; ++t)
-          if (t < tail) l += ex2_approx(fmaf(st[t], scale_log2, -m2));
-      }
+    if (tail > 0) {  // (finishes while the first S tile is still being loaded / multiplied)
+      mbar_wait(&sm->q_full, 0);     // the Q tile has landed (TMA complete_tx)
+      mbar_wait(&sm->tail_full, 0);  // ... and the tail key's rows
+      m2 = tail_score() * scale_log2;
+      if (hf == 0) l = 1.0f;  // ex2(0); the partners' row sums are added at the end: only one of them counts the tail
     }
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&sm->s_full, (uint32_t)j & 1u);
@@ -299,6 +294,11 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
     sm->xchg[nkv & 1][hf][r] = l;
     asm volatile("bar.sync 2, 256;" ::: "memory");
     l += sm->xchg[nkv & 1][hf ^ 1][r];
+    float pt = 0.f;  // tail key's probability, computed while the last P V MMA is still in flight
+    if (tail > 0) {
+      pt = ex2_approx(fmaf(tail_score(), scale_log2, -m2));
+      if (kDrop && !drop_keep(drop, rowe + (unsigned long long)Nk)) pt = 0.f;
+    }
     mbar_wait(&sm->pv_done, (uint32_t)(nkv - 1) & 1u);
     tc_fence_after();
     const float inv = (kDrop ? drop.inv_keep : 1.0f) / l;
@@ -307,27 +307,19 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
       uint32_t o[32];
       tmem_ld32(tO + lane_off + hf * 32, o);
       tmem_ld_wait();
-      if (tail > 0 && q < N) {  // P V of the tail keys (dropout keep factor included; 1/(1-p) rides on `inv`)
-        float st[kMaxAttnTail];
-        tail_scores(st);
+      if (tail > 0 && q < N) {  // P V of the tail key (dropout keep factor included; 1/(1-p) rides on `inv`)
+        const uint32_t vrow = smem_u32(&sm->tail_kv[8]) + (uint32_t)hf * 64u;
 #pragma unroll
-        for (int t = 0; t < kMaxAttnTail; ++t)
-          if (t < tail) {
-            float pt = ex2_approx(fmaf(st[t], scale_log2, -m2));
-            if (kDrop && !drop_keep(drop, rowe + (unsigned long long)(Nk + t))) pt = 0.f;
-            const __nv_bfloat16* vrow = qkv + ((long long)b * N + Nk + t) * (3LL * D) + 2 * D + h * kHd + hf * 32;
+        for (int c = 0; c < 4; ++c) {
+          const uint4 vv = ld_shared_u4(vrow + 16 * c);
+          const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vrow + 8 * c));
-              const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[i]));
-                o[8 * c + 2 * i] = __float_as_uint(fmaf(pt, f.x, __uint_as_float(o[8 * c + 2 * i])));
-                o[8 * c + 2 * i + 1] = __float_as_uint(fmaf(pt, f.y, __uint_as_float(o[8 * c + 2 * i + 1])));
-              }
-            }
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[i]));
+            o[8 * c + 2 * i] = __float_as_uint(fmaf(pt, f.x, __uint_as_float(o[8 * c + 2 * i])));
+            o[8 * c + 2 * i + 1] = __float_as_uint(fmaf(pt, f.y, __uint_as_float(o[8 * c + 2 * i + 1])));
           }
+        }
       }
       if (q < N) {
 #pragma unroll
@@ -363,7 +355,7 @@ int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int
   if (hd != kHd) return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 attention supports head_dim 64 only (got %d)", hd);
   const int D = H * hd;
   if (D % 8 != 0) return fail(TVIT_ERR_BAD_ARG, "attention: embed dim must be a multiple of 8");
-  constexpr int smem_bytes = 5 * kTileBytes + 1024 + 256 + 2048;  // tiles + alignment + barriers + partner exchange
+  constexpr int smem_bytes = 5 * kTileBytes + 1024 + 256 + 2048 + 512;  // tiles + alignment + barriers + exchange + tail
   int rc;
   if ((rc = ensure_dynamic_smem((const void*)tc_attn_fwd_kernel<false>, smem_bytes)) != TVIT_OK) return rc;
   if ((rc = ensure_dynamic_smem((const void*)tc_attn_fwd_kernel<true>, smem_bytes)) != TVIT_OK) return rc;
@@ -372,7 +364,7 @@ int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int
   dim3 grid((N + kTile - 1) / kTile, H, B);
   const float scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
   const DropCfg dc = make_drop(drop);
-  const int tail = attn_tail(N);
+  const int tail = attn_tail(N, 1);
   const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv;
   if (dc.thr16 != 0)
     tc_attn_fwd_kernel<true><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, qp, (__nv_bfloat16*)out, lse, N, tail, H, scale_log2, dc);

@@ -24,9 +24,12 @@
 //
 // Ragged tail: when N = 128 m + t with a small t (N = 2049 = 16 * 128 + 1 at the bench shape), the last t QUERIES are
 // not given a query tile of their own (one more trip through the five-MMA loop for one valid row: 1/17 of the kernel).
-// Every key-tile CTA handles them in its epilogue on the CUDA cores, thread == key row with K_j / V_j still in shared
-// memory: s = q_t . k, dP = dO_t . v, dS as in the loop; dK_j / dV_j get the rank-1 updates before they are stored and
-// the partial dQ_t = sum_k dS k is warp-reduced and added to the same fp32 accumulator the drained dQ tiles go to.
+// Every key-tile CTA handles the tail query on the CUDA cores, thread == key row with K_j / V_j in shared memory:
+// s = q_t . k, dP = dO_t . v, dS as in the loop.  The four dQ-drain warps -- idle most of the time -- do this at the
+// START of the kernel, overlapped with the tile loop: they leave dS / (P mask) per key row in shared memory and add the
+// warp-reduced partial dQ_t = sum_k dS k to the same fp32 accumulator the drained dQ tiles go to; the softmax warps
+// only apply the rank-1 updates dK_j += dS q_t, dV_j += (P mask) dO_t right before they store dK_j / dV_j.
+// (A first version did all of it in the epilogue, where nothing overlaps it: it cost as much as the tile it saved.)
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -87,9 +90,12 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
 constexpr int kQStages = 3;  // Q / dO tiles in flight
 struct AttnBwdSmem {
   uint64_t kv_full, qdo_full[kQStages], qdo_empty[kQStages], s_full[2], s_free[2], p_full, p_free, ds_free[2], dq_full,
-      dq_free, tds_free;
+      dq_free, tds_free, tail_ready;
   uint32_t tmem_base;
+  uint32_t pad_;
+  float tail_ds[kTileB], tail_pm[kTileB];  // tail query (see header): dS and masked P of this CTA's 128 key rows
 };
+static_assert(sizeof(AttnBwdSmem) <= 1280, "AttnBwdSmem must fit the 1.25 KB tail of the dynamic smem block");
 
 // Dvec[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
@@ -203,6 +209,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_init(&sm->tds_free, 1);
     mbar_init(&sm->dq_full, 1);
     mbar_init(&sm->dq_free, 128);
+    mbar_init(&sm->tail_ready, 128);
     fence_barrier_init();
   }
   if (warp == 21) {
@@ -439,60 +446,21 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       uint32_t o[32];
       tmem_ld32(tsrc + lane_off + c * 32, o);
       tmem_ld_wait();
-      for (int t = 0; t < tail; ++t) {  // ---- tail queries (see header): thread == key row kv ----
-        const int qi = Nq + t;
-        const __nv_bfloat16* qrow = qkv + ((long long)b * N + qi) * (3LL * D) + h * kHdB;
-        const __nv_bfloat16* dorow = dout + ((long long)b * N + qi) * D + h * kHdB;
-        const uint32_t krow = smem_u32(sK) + (uint32_t)r * 128u, vrow = smem_u32(sV) + (uint32_t)r * 128u;
-        float sc = 0.f, dpv = 0.f;
+      if (tail > 0) {  // ---- tail query (see header): rank-1 updates with the values the drain warps left in smem ----
+        const int qi = Nq;
+        mbar_wait(&sm->tail_ready, 0);
+        const float f = which == 0 ? sm->tail_ds[r] : sm->tail_pm[r];
+        const __nv_bfloat16* src = (which == 0 ? qkv + ((long long)b * N + qi) * (3LL * D) + h * kHdB
+                                               : dout + ((long long)b * N + qi) * D + h * kHdB) + c * 32;
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {  // 16-byte pieces of the 128B-swizzled K / V rows
-          const uint32_t sw = (uint32_t)((cc ^ (r & 7)) * 16);
-          sc = dot8_bf16(ld_shared_u4(krow + sw), __ldg(reinterpret_cast<const uint4*>(qrow + 8 * cc)), sc);
-          dpv = dot8_bf16(ld_shared_u4(vrow + sw), __ldg(reinterpret_cast<const uint4*>(dorow + 8 * cc)), dpv);
-        }
-        float pt = ex2_approx(fmaf(sc, c_log2, -lse_bh[qi] * 1.4426950408889634f));
-        float mlt = 1.0f;
-        if (kDrop) mlt = drop_keep(drop, attn_drop_row_base(b, H, h, N, qi) + (unsigned long long)kv) ? drop.inv_keep : 0.f;
-        float dst = pt * (dpv * mlt - dv_bh[qi]) * scale, pmt = pt * mlt;
-        if (kv >= N) dst = pmt = 0.f;
-        {  // rank-1 updates of this thread's 32 columns: dK += dS q_t, dV += (P mask) dO_t
-          const __nv_bfloat16* src = (which == 0 ? qrow : dorow) + c * 32;
-          const float f = which == 0 ? dst : pmt;
+        for (int cc = 0; cc < 4; ++cc) {
+          const uint4 vv = __ldg(reinterpret_cast<const uint4*>(src + 8 * cc));
+          const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const uint4 vv = __ldg(reinterpret_cast<const uint4*>(src + 8 * cc));
-            const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[i]));
-              o[8 * cc + 2 * i] = __float_as_uint(fmaf(f, g.x, __uint_as_float(o[8 * cc + 2 * i])));
-              o[8 * cc + 2 * i + 1] = __float_as_uint(fmaf(f, g.y, __uint_as_float(o[8 * cc + 2 * i + 1])));
-            }
-          }
-        }
-        if (chunk == 0) {  // dQ_t += sum over this warp's 32 key rows of dS k: one warp per lane quarter
-          float* trow = dqacc + (((long long)b * H + h) * nqt + nq) * (16LL * 128 * 4) + t * 4;
-#pragma unroll 1
-          for (int cc = 0; cc < 8; ++cc) {
-            const uint4 kk = ld_shared_u4(krow + (uint32_t)((cc ^ (r & 7)) * 16));
-            const uint32_t kw[4] = {kk.x, kk.y, kk.z, kk.w};
-            float v8[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[i]));
-              v8[2 * i] = dst * g.x;
-              v8[2 * i + 1] = dst * g.y;
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v8[i] += __shfl_xor_sync(0xffffffffu, v8[i], off);
-            float val = v8[0];
-#pragma unroll
-            for (int i = 1; i < 8; ++i) val = (lane == i) ? v8[i] : val;
-            // column d = 8 cc + lane of accumulator row t: chunk d / 4, element d % 4
-            if (lane < 8) atomicAdd(trow + (2 * cc + (lane >> 2)) * 512 + (lane & 3), val);
+          for (int i = 0; i < 4; ++i) {
+            const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[i]));
+            o[8 * cc + 2 * i] = __float_as_uint(fmaf(f, g.x, __uint_as_float(o[8 * cc + 2 * i])));
+            o[8 * cc + 2 * i + 1] = __float_as_uint(fmaf(f, g.y, __uint_as_float(o[8 * cc + 2 * i + 1])));
           }
         }
       }
@@ -540,6 +508,55 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                                 __uint_as_float(o[4 * c + 3])));
         }
       }
+      if (i == 0 && tail > 0) {  // ---- tail query (see header): thread == key row kv0 + r.  Done in the idle gap
+          // after the FIRST drain: before it, it would delay dq_free of tile 0 and with it the whole MMA pipeline ----
+        const int qi = Nq, kv = kv0 + r;
+        const float c_log2 = scale * 1.4426950408889634f;
+        const __nv_bfloat16* qrow = qkv + ((long long)b * N + qi) * (3LL * D) + h * kHdB;
+        const __nv_bfloat16* dorow = dout + ((long long)b * N + qi) * D + h * kHdB;
+        const float lse_t = lse[((long long)b * H + h) * N + qi], d_t = dvec[((long long)b * H + h) * N + qi];
+        mbar_wait(&sm->kv_full, 0);
+        const uint32_t krow = smem_u32(sK) + (uint32_t)r * 128u, vrow = smem_u32(sV) + (uint32_t)r * 128u;
+        float sc = 0.f, dpv = 0.f;
+  #pragma unroll 2
+        for (int cc = 0; cc < 8; ++cc) {  // 16-byte pieces of the 128B-swizzled K / V rows (these warps are idle anyway:
+                                          // the L2 latency of the broadcast q_t / dO_t loads is not on the critical path)
+          const uint32_t sw = (uint32_t)((cc ^ (r & 7)) * 16);
+          sc = dot8_bf16(ld_shared_u4(krow + sw), __ldg(reinterpret_cast<const uint4*>(qrow + 8 * cc)), sc);
+          dpv = dot8_bf16(ld_shared_u4(vrow + sw), __ldg(reinterpret_cast<const uint4*>(dorow + 8 * cc)), dpv);
+        }
+        const float pt = ex2_approx(fmaf(sc, c_log2, -lse_t * 1.4426950408889634f));
+        float mlt = 1.0f;
+        if (kDrop) mlt = drop_keep(drop, attn_drop_row_base(b, H, h, N, qi) + (unsigned long long)kv) ? drop.inv_keep : 0.f;
+        float dst = pt * (dpv * mlt - d_t) * scale, pmt = pt * mlt;
+        if (kv >= N) dst = pmt = 0.f;
+        sm->tail_ds[r] = dst;
+        sm->tail_pm[r] = pmt;
+        mbar_arrive(&sm->tail_ready);
+        // dQ_t += sum over this warp's 32 key rows of dS k  (accumulator tile nq, row 0)
+        float* trow = acc_bh + (long long)nq * (16 * 128 * 4);
+  #pragma unroll 1
+        for (int cc = 0; cc < 8; ++cc) {
+          const uint4 kk = ld_shared_u4(krow + (uint32_t)((cc ^ (r & 7)) * 16));
+          const uint32_t kw[4] = {kk.x, kk.y, kk.z, kk.w};
+          float v8[8];
+  #pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[i]));
+            v8[2 * i] = dst * g.x;
+            v8[2 * i + 1] = dst * g.y;
+          }
+  #pragma unroll
+          for (int off = 16; off > 0; off >>= 1)
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) v8[i] += __shfl_xor_sync(0xffffffffu, v8[i], off);
+          float val = v8[0];
+  #pragma unroll
+          for (int i = 1; i < 8; ++i) val = (lane == i) ? v8[i] : val;
+          // column d = 8 cc + lane of accumulator row 0: chunk d / 4, element d % 4
+          if (lane < 8) atomicAdd(trow + (2 * cc + (lane >> 2)) * 512 + (lane & 3), val);
+        }
+      }
     }
   }
 
@@ -580,7 +597,7 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   float* dqacc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + ws_dvec_bytes(B, N, H));
   const size_t dq_bytes = (size_t)B * H * nq * 16 * 128 * 4 * sizeof(float);
 
-  constexpr int smem_bytes = 2 * kTileBytesB + kQStages * 2 * kTileBytesB + 3 * kPBytes + 1024 + 256;  // 225.25 KB
+  constexpr int smem_bytes = 2 * kTileBytesB + kQStages * 2 * kTileBytesB + 3 * kPBytes + 1024 + 1280;  // 226.25 KB
   int rc;
   if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false>, smem_bytes)) != TVIT_OK) return rc;
   if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true>, smem_bytes)) != TVIT_OK) return rc;
@@ -598,7 +615,7 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   dim3 grid(nq, H, B);
   const float scale = 1.0f / sqrtf((float)hd);
   const DropCfg dc = make_drop(drop);
-  const int tail = attn_tail(N);
+  const int tail = attn_tail(N, 2);
   const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv;
   const __nv_bfloat16* dop = (const __nv_bfloat16*)dout;
   if (dc.thr16 != 0)
