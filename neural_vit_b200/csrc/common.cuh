@@ -356,12 +356,12 @@ __device__ __forceinline__ void drop_keep_masks16(const DropCfg& c, unsigned lon
 
 // Ragged tail of the tcgen05 attention kernels: when N = 128 m + 1 (the CLS token: N = 2049, 16385, ...), the last key
 // (forward) / query (backward) can be handled on the CUDA cores instead of through an almost empty 128-wide tile.
-// Measured at the bench shape (profiles/r2_kern_v13_tail.log): forward -4 % without dropout, -2 % with it (default ON);
-// backward +1.5 ... +2.7 % even with the tail work hidden on the idle dQ-drain warps (default OFF).
-// TVIT_ATTN_TAIL = bit 0: forward, bit 1: backward (A-B timing / debugging).
+// Measured at the bench shape: forward -4 % without dropout, -2 % with it (profiles/r2_kern_v13_tail.log); backward
+// -3.3 % / -3.7 % once the tail work runs on the two idle warps (profiles/r2_kern_v14_tail_bwd.log).  Both default ON.
+// TVIT_ATTN_TAIL = bit 0: forward, bit 1: backward (A-B timing / debugging); 0 disables both.
 constexpr int kMaxAttnTail = 1;
 inline int attn_tail_mask() {
-  static const int m = [] { const char* e = getenv("TVIT_ATTN_TAIL"); return e ? atoi(e) : 1; }();
+  static const int m = [] { const char* e = getenv("TVIT_ATTN_TAIL"); return e ? atoi(e) : 3; }();
   return m;
 }
 inline int attn_tail(int N, int pass_bit) {

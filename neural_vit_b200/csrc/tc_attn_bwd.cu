@@ -25,11 +25,11 @@
 // Ragged tail: when N = 128 m + t with a small t (N = 2049 = 16 * 128 + 1 at the bench shape), the last t QUERIES are
 // not given a query tile of their own (one more trip through the five-MMA loop for one valid row: 1/17 of the kernel).
 // Every key-tile CTA handles the tail query on the CUDA cores, thread == key row with K_j / V_j in shared memory:
-// s = q_t . k, dP = dO_t . v, dS as in the loop.  The four dQ-drain warps -- idle most of the time -- do this at the
-// START of the kernel, overlapped with the tile loop: they leave dS / (P mask) per key row in shared memory and add the
-// warp-reduced partial dQ_t = sum_k dS k to the same fp32 accumulator the drained dQ tiles go to; the softmax warps
-// only apply the rank-1 updates dK_j += dS q_t, dV_j += (P mask) dO_t right before they store dK_j / dV_j.
-// (A first version did all of it in the epilogue, where nothing overlaps it: it cost as much as the tile it saved.)
+// s = q_t . k, dP = dO_t . v, dS as in the loop.  The two otherwise idle warps 22-23 do this concurrently with the tile
+// loop: they leave dS / (P mask) per key row in shared memory and add the warp-reduced partial dQ_t = sum_k dS k to the
+// same fp32 accumulator the drained dQ tiles go to; the softmax warps only apply the rank-1 updates dK_j += dS q_t,
+// dV_j += (P mask) dO_t right before they store dK_j / dV_j.  (Doing it in the epilogue cost as much as the tile it
+// saved; doing it on the dQ-drain warps delayed dq_free and with it the MMA pipeline: +7 %.)
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -40,7 +40,7 @@ constexpr int kHdB = 64;
 constexpr int kTileB = 128;
 constexpr int kTileBytesB = kTileB * kHdB * 2;  // 16384: one [128 x 64] bf16 operand tile
 constexpr int kPBytes = kTileB * kTileB * 2;    // 32768: one [128 x 128] bf16 P / dS tile (two 64-wide blocks)
-constexpr int kAttnBwdThreads = 768;  // warps 0-15 softmax, 16-19 dQ drain, 20 TMA, 21 MMA (+TMEM alloc), 22-23 idle
+constexpr int kAttnBwdThreads = 768;  // warps 0-15 softmax, 16-19 dQ drain, 20 TMA, 21 MMA (+TMEM alloc), 22-23 tail query
 constexpr int kSoftmaxWarps = 16;
 
 __device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b, float acc) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1)
 tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ dvec, float* __restrict__ dqacc,
-                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int N, int tail, int H, float scale,
+                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int N, int tail_arg, int H, float scale,
                    DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -189,6 +189,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int D = H * kHdB;
   const int kv0 = jt * kTileB;
+  const int dbg = tail_arg >> 8, tail = tail_arg & 0xff;  // dbg: timing experiments only (TVIT_ATTN_TAIL_DBG)
   const int nqt = (N + kTileB - 1) / kTileB;  // query tiles of the dQ accumulator
   const int Nq = N - tail;                    // queries that go through the tile loop
   const int nq = (Nq + kTileB - 1) / kTileB;  // tiles in the loop (== nqt unless there is a tail)
@@ -209,7 +210,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_init(&sm->tds_free, 1);
     mbar_init(&sm->dq_full, 1);
     mbar_init(&sm->dq_free, 128);
-    mbar_init(&sm->tail_ready, 128);
+    mbar_init(&sm->tail_ready, 64);
     fence_barrier_init();
   }
   if (warp == 21) {
@@ -446,7 +447,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       uint32_t o[32];
       tmem_ld32(tsrc + lane_off + c * 32, o);
       tmem_ld_wait();
-      if (tail > 0) {  // ---- tail query (see header): rank-1 updates with the values the drain warps left in smem ----
+      if (tail > 0 && !(dbg & 2)) {  // ---- tail query (see header): rank-1 updates with the values the drain warps left in smem ----
         const int qi = Nq;
         mbar_wait(&sm->tail_ready, 0);
         const float f = which == 0 ? sm->tail_ds[r] : sm->tail_pm[r];
@@ -508,19 +509,27 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                                 __uint_as_float(o[4 * c + 3])));
         }
       }
-      if (i == 0 && tail > 0) {  // ---- tail query (see header): thread == key row kv0 + r.  Done in the idle gap
-          // after the FIRST drain: before it, it would delay dq_free of tile 0 and with it the whole MMA pipeline ----
-        const int qi = Nq, kv = kv0 + r;
-        const float c_log2 = scale * 1.4426950408889634f;
-        const __nv_bfloat16* qrow = qkv + ((long long)b * N + qi) * (3LL * D) + h * kHdB;
-        const __nv_bfloat16* dorow = dout + ((long long)b * N + qi) * D + h * kHdB;
-        const float lse_t = lse[((long long)b * H + h) * N + qi], d_t = dvec[((long long)b * H + h) * N + qi];
-        mbar_wait(&sm->kv_full, 0);
+    }
+  } else if (warp >= 22) {
+    // ============================ tail-query warps (22-23; see header) ============================
+    // Two otherwise idle warps: thread == key rows kv0 + r and kv0 + r + 64.  They are not part of the tile pipeline,
+    // so the latency of their global loads costs nothing (on the dQ-drain warps the same work delayed dq_free of the
+    // following tile and cost 7 % of the kernel: profiles/r2_kern_v14_tail_bwd.log).
+    if (tail > 0 && !(dbg & 1)) {
+      const int qi = Nq;
+      const float c_log2 = scale * 1.4426950408889634f;
+      const __nv_bfloat16* qrow = qkv + ((long long)b * N + qi) * (3LL * D) + h * kHdB;
+      const __nv_bfloat16* dorow = dout + ((long long)b * N + qi) * D + h * kHdB;
+      const float lse_t = lse[((long long)b * H + h) * N + qi], d_t = dvec[((long long)b * H + h) * N + qi];
+      mbar_wait(&sm->kv_full, 0);
+      float dsr[2];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = (warp - 22) * 32 + lane + 64 * rr, kv = kv0 + r;
         const uint32_t krow = smem_u32(sK) + (uint32_t)r * 128u, vrow = smem_u32(sV) + (uint32_t)r * 128u;
         float sc = 0.f, dpv = 0.f;
-  #pragma unroll 2
-        for (int cc = 0; cc < 8; ++cc) {  // 16-byte pieces of the 128B-swizzled K / V rows (these warps are idle anyway:
-                                          // the L2 latency of the broadcast q_t / dO_t loads is not on the critical path)
+#pragma unroll 4
+        for (int cc = 0; cc < 8; ++cc) {  // 16-byte pieces of the 128B-swizzled K / V rows
           const uint32_t sw = (uint32_t)((cc ^ (r & 7)) * 16);
           sc = dot8_bf16(ld_shared_u4(krow + sw), __ldg(reinterpret_cast<const uint4*>(qrow + 8 * cc)), sc);
           dpv = dot8_bf16(ld_shared_u4(vrow + sw), __ldg(reinterpret_cast<const uint4*>(dorow + 8 * cc)), dpv);
@@ -532,31 +541,42 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (kv >= N) dst = pmt = 0.f;
         sm->tail_ds[r] = dst;
         sm->tail_pm[r] = pmt;
-        mbar_arrive(&sm->tail_ready);
-        // dQ_t += sum over this warp's 32 key rows of dS k  (accumulator tile nq, row 0)
-        float* trow = acc_bh + (long long)nq * (16 * 128 * 4);
-  #pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {
-          const uint4 kk = ld_shared_u4(krow + (uint32_t)((cc ^ (r & 7)) * 16));
+        dsr[rr] = dst;
+      }
+      mbar_arrive(&sm->tail_ready);
+      // dQ_t += sum over this warp's 64 key rows of dS k  (accumulator tile nq, row 0)
+      float* trow = dqacc + (((long long)b * H + h) * nqt + nq) * (16LL * 128 * 4);
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        float v8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v8[i] = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = (warp - 22) * 32 + lane + 64 * rr;
+          const uint4 kk = ld_shared_u4(smem_u32(sK) + (uint32_t)r * 128u + (uint32_t)((cc ^ (r & 7)) * 16));
           const uint32_t kw[4] = {kk.x, kk.y, kk.z, kk.w};
-          float v8[8];
-  #pragma unroll
+#pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[i]));
-            v8[2 * i] = dst * g.x;
-            v8[2 * i + 1] = dst * g.y;
+            v8[2 * i] = fmaf(dsr[rr], g.x, v8[2 * i]);
+            v8[2 * i + 1] = fmaf(dsr[rr], g.y, v8[2 * i + 1]);
           }
-  #pragma unroll
-          for (int off = 16; off > 0; off >>= 1)
-  #pragma unroll
-            for (int i = 0; i < 8; ++i) v8[i] += __shfl_xor_sync(0xffffffffu, v8[i], off);
-          float val = v8[0];
-  #pragma unroll
-          for (int i = 1; i < 8; ++i) val = (lane == i) ? v8[i] : val;
-          // column d = 8 cc + lane of accumulator row 0: chunk d / 4, element d % 4
-          if (lane < 8) atomicAdd(trow + (2 * cc + (lane >> 2)) * 512 + (lane & 3), val);
         }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v8[i] += __shfl_xor_sync(0xffffffffu, v8[i], off);
+        float val = v8[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) val = (lane == i) ? v8[i] : val;
+        // column d = 8 cc + lane of accumulator row 0: chunk d / 4, element d % 4
+        if (lane < 8) atomicAdd(trow + (2 * cc + (lane >> 2)) * 512 + (lane & 3), val);
       }
+    } else if (tail > 0) {  // timing experiment: no tail work
+      sm->tail_ds[(warp - 22) * 32 + lane] = sm->tail_ds[(warp - 22) * 32 + lane + 64] = 0.f;
+      sm->tail_pm[(warp - 22) * 32 + lane] = sm->tail_pm[(warp - 22) * 32 + lane + 64] = 0.f;
+      mbar_arrive(&sm->tail_ready);
     }
   }
 
@@ -615,7 +635,8 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   dim3 grid(nq, H, B);
   const float scale = 1.0f / sqrtf((float)hd);
   const DropCfg dc = make_drop(drop);
-  const int tail = attn_tail(N, 2);
+  int tail = attn_tail(N, 2);
+  if (const char* e = getenv("TVIT_ATTN_TAIL_DBG")) tail |= atoi(e) << 8;
   const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv;
   const __nv_bfloat16* dop = (const __nv_bfloat16*)dout;
   if (dc.thr16 != 0)
