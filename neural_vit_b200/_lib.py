@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtvit_b200.so")
+LIB_PATH = os.environ.get("TVIT_LIB_PATH") or os.path.join(_HERE, "libtvit_b200.so")   # override: A/B builds only
 
 F32, BF16 = 0, 1
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1

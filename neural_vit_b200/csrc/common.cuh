@@ -213,6 +213,9 @@ template <typename T> __device__ __forceinline__ float gelu_grad_t(float x) {
 // part of the generator every element is dropped with probability exactly thr16 / 65536; the elements of one
 // group share T_g, a correlation of about 4e-5.
 // ---------------------------------------------------------------------------------------------
+#ifndef TVIT_PHILOX_ROUNDS
+#define TVIT_PHILOX_ROUNDS 7
+#endif
 struct DropCfg {
   unsigned long long seed;
   unsigned int site;   // unique per dropout call site within one forward
@@ -227,7 +230,7 @@ __host__ __device__ __forceinline__ DropCfg make_drop(const tvit_dropout* d) {
   DropCfg c;
   c.seed = d ? d->seed : 0ull;
   c.site = d ? d->site : 0u;
-  for (int r = 0; r < 7; ++r) {
+  for (int r = 0; r < TVIT_PHILOX_ROUNDS; ++r) {
     c.rk0[r] = (unsigned int)c.seed + (unsigned int)r * 0x9E3779B9u;
     c.rk1[r] = (unsigned int)(c.seed >> 32) + (unsigned int)r * 0xBB67AE85u;
   }
@@ -248,7 +251,7 @@ __device__ __forceinline__ uint4 philox4x32_7(unsigned long long seed, unsigned 
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = site, c3 = 0x5eed5eedu;
 #pragma unroll
-  for (int r = 0; r < 7; ++r) {
+  for (int r = 0; r < TVIT_PHILOX_ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ k0;
@@ -265,7 +268,7 @@ __device__ __forceinline__ uint4 philox4x32_7(unsigned long long seed, unsigned 
 __device__ __forceinline__ uint4 philox4x32_7(const DropCfg& c, unsigned long long ctr) {
   uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = c.site, c3 = 0x5eed5eedu;
 #pragma unroll
-  for (int r = 0; r < 7; ++r) {
+  for (int r = 0; r < TVIT_PHILOX_ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ c.rk0[r];
