@@ -392,18 +392,13 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (lane == 0) mbar_arrive(&sm->s_free[hf]);  // this half's S / dP columns may be refilled
         uint32_t pk[8], dk[8];
         uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0;
-        if (kDrop && !(dbg & 16)) {  // this thread's 16 keys are exactly one Philox group (common.cuh)
+        if (kDrop) {  // this thread's 16 keys are exactly one Philox group (common.cuh)
           const unsigned long long grp = (rowe >> 4) + (unsigned long long)(hf * 4 + chunk);
           drop_bits16(drop, grp, w);
           tg2 = drop_tgc(drop_thr8(drop, grp));
         }
 #pragma unroll
         for (int t = 0; t < 8; ++t) {  // element pairs (2t, 2t+1)
-          if (dbg & 16) {  // timing experiment: no softmax math
-            pk[t] = sv[2 * t];
-            dk[t] = dp[2 * t];
-            continue;
-          }
           const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * t]), c_log2, -lse2));
           const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * t + 1]), c_log2, -lse2));
           const float a0 = fmaf(__uint_as_float(dp[2 * t]), scale, negDq);
@@ -423,11 +418,11 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           if (i >= 1) mbar_wait(&sm->p_free, (uint32_t)(i - 1) & 1u);  // dV_{i-1} has read sP
           if (i >= 2) mbar_wait(&sm->ds_free[i & 1], (((uint32_t)i >> 1) - 1u) & 1u);  // tile i-2 has read this sDS
         }
-        if (kTsDq && !(dbg & 8)) tmem_st8(tDS + lane_off + hf * 32 + chunk * 8, dk);  // dS for the dQ MMA (A operand from TMEM)
+        if (kTsDq) tmem_st8(tDS + lane_off + hf * 32 + chunk * 8, dk);  // dS for the dQ MMA (A operand from TMEM)
         // row r of 64-key block hf: 16-byte pieces chunk * 2 + g, XOR-swizzled with (r & 7)
         const uint32_t row_off = (uint32_t)hf * 16384u + (uint32_t)r * 128u;
 #pragma unroll
-        for (int g = 0; g < 2 && !(dbg & 8); ++g) {
+        for (int g = 0; g < 2; ++g) {
           const uint32_t piece = (uint32_t)((chunk * 2 + g) ^ (r & 7)) * 16u;
           st_shared_v4(smem_u32(sP) + row_off + piece, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           st_shared_v4(aDSbuf + row_off + piece, dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
@@ -507,7 +502,6 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           tc_fence_before();
           mbar_arrive(&sm->dq_free);
         }
-        if (dbg & 4) continue;  // timing experiment: no dQ reductions
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           atomicAdd(reinterpret_cast<float4*>(tile + (hc * 8 + c) * 512),
