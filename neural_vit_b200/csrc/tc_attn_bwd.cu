@@ -36,6 +36,9 @@
 
 namespace tvit {
 
+#ifndef TVIT_ATTN_BWD_T_DEFAULT
+#define TVIT_ATTN_BWD_T_DEFAULT 0
+#endif
 constexpr int kHdB = 64;
 constexpr int kTileB = 128;
 constexpr int kTileBytesB = kTileB * kHdB * 2;  // 16384: one [128 x 64] bf16 operand tile
@@ -87,10 +90,68 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// 1-D bulk copy global -> shared (16-byte aligned, size % 16 == 0), completion counted on an mbarrier like a TMA load
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint32_t prmt_r(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// Dropout keep flags of one Philox group as sign bits: bit 7 of byte j of w[] ends up set iff byte j >= thr8
+// (thr8 in [0, 256]); the other bits are don't-care.  Four bytes per SWAR step: r = (w | 0x80..) - low7(T) has bit 7 of a
+// byte set iff low7(byte) >= low7(T) (no borrow can cross bytes), and byte >= T <=> T < 128 ? (b7 | r7) : (b7 & r7);
+// T = 256 (keep nothing) is mapped to low7 = 0x80, which clears r7.
+__device__ __forceinline__ void drop_keep_sign16(uint32_t (&w)[4], uint32_t thr8) {
+  const uint32_t tl = ((thr8 & 0x7fu) | ((thr8 >> 1) & 0x80u)) * 0x01010101u;
+  const uint32_t tm = thr8 >= 128u ? 0xffffffffu : 0u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t r = (w[k] | 0x80808080u) - tl;
+    w[k] = (tm & w[k] & r) | (~tm & (w[k] | r));
+  }
+}
+// In-register transpose of a 16 x 16 byte matrix held by the 16 lanes of each half-warp (lane i: row i, byte j of
+// w[j >> 2] = element (i, j)): two word-granular butterflies (lane bits 3, 2 <-> word index bits) and two byte-granular
+// ones (lane bits 1, 0 <-> byte index bits, prmt picks own / received bytes).  12 shuffles, 20 ALU instructions.
+__device__ __forceinline__ void transpose16x16_bytes(uint32_t (&w)[4], int lane) {
+  {
+    const bool hi = (lane & 8) != 0;
+    const uint32_t s0 = __shfl_xor_sync(0xffffffffu, hi ? w[0] : w[2], 8);
+    const uint32_t s1 = __shfl_xor_sync(0xffffffffu, hi ? w[1] : w[3], 8);
+    w[0] = hi ? s0 : w[0]; w[1] = hi ? s1 : w[1]; w[2] = hi ? w[2] : s0; w[3] = hi ? w[3] : s1;
+  }
+  {
+    const bool hi = (lane & 4) != 0;
+    const uint32_t s0 = __shfl_xor_sync(0xffffffffu, hi ? w[0] : w[1], 4);
+    const uint32_t s1 = __shfl_xor_sync(0xffffffffu, hi ? w[2] : w[3], 4);
+    w[0] = hi ? s0 : w[0]; w[2] = hi ? s1 : w[2]; w[1] = hi ? w[1] : s0; w[3] = hi ? w[3] : s1;
+  }
+  {
+    const uint32_t sel = (lane & 2) ? 0x3276u : 0x5410u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = prmt_r(w[k], __shfl_xor_sync(0xffffffffu, w[k], 2), sel);
+  }
+  {
+    const uint32_t sel = (lane & 1) ? 0x3715u : 0x6240u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = prmt_r(w[k], __shfl_xor_sync(0xffffffffu, w[k], 1), sel);
+  }
+}
+
 constexpr int kQStages = 3;  // Q / dO tiles in flight
 struct AttnBwdSmem {
   uint64_t kv_full, qdo_full[kQStages], qdo_empty[kQStages], s_full[2], s_free[2], p_full, p_free, ds_free[2], dq_full,
-      dq_free, tds_free, tail_ready;
+      dq_free, tds_free, tail_ready, pt_full[2];
   uint32_t tmem_base;
   uint32_t pad_;
   float tail_ds[kTileB], tail_pm[kTileB];  // tail query (see header): dS and masked P of this CTA's 128 key rows
@@ -122,6 +183,26 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const 
     }
   }
   dvec[((long long)b * H + h) * N + q] = s;
+}
+
+// Column statistics of the transposed kernel, one 1 KB record per (b, h, query tile): [-lse2 x 128 | -D' x 128] with
+// lse2 = lse log2(e) - log2(1/(1-p)) and D' = D scale (1-p); rows past N get -inf / 0 so that their P is exactly 0.
+__global__ void attn_bwd_stat_kernel(const float* __restrict__ lse, const float* __restrict__ dvec,
+                                     float* __restrict__ stat, int BH, int N, int nqt, float log2_inv_keep,
+                                     float d_scale) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)BH * nqt * kTileB) return;
+  const int r = (int)(idx & (kTileB - 1));
+  const long long t = idx >> 7;  // bh * nqt + tile
+  const int q = (int)(t % nqt) * kTileB + r;
+  const long long bh = t / nqt;
+  float nl = -INFINITY, nd = 0.f;
+  if (q < N) {
+    nl = log2_inv_keep - lse[bh * N + q] * 1.4426950408889634f;
+    nd = -dvec[bh * N + q] * d_scale;
+  }
+  stat[t * 256 + r] = nl;
+  stat[t * 256 + 128 + r] = nd;
 }
 
 // dq accumulator layout: [(b*H+h)][q tile][16 chunks][128 rows][4 fp32]
@@ -162,13 +243,17 @@ __global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_
   }
 }
 
-template <bool kDrop>
+// kT selects the transposed formulation (see the header): S^T = K_j Q_i^T and dP^T = V_j dO_i^T land in TMEM with
+// thread == key row, so that P^T and dS^T -- written back in place as bf16 -- are the TMEM A operands of the dV / dK
+// MMAs, and only dS^T goes through shared memory (for dQ).  `stat` holds the per-query column statistics
+// [(b,h)][q tile][-lse2 x 128 | -D' x 128] produced by attn_bwd_stat_kernel (kT only).
+template <bool kDrop, bool kT>
 __global__ void __launch_bounds__(kAttnBwdThreads, 1)
 tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
-                   const float* __restrict__ lse, const float* __restrict__ dvec, float* __restrict__ dqacc,
-                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int N, int tail_arg, int H, float scale,
-                   DropCfg drop) {
+                   const float* __restrict__ lse, const float* __restrict__ dvec, const float* __restrict__ stat,
+                   float* __restrict__ dqacc, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int N,
+                   int tail_arg, int H, float scale, DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;
@@ -177,13 +262,14 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sP = sQdO + kQStages * 2 * kTileBytesB;   // P  [2 key blocks][128 q rows][64 keys], single buffer
   uint8_t* sDS = sP + kPBytes;                       // dS, same layout, buffer u (= tile parity) at +u*32K
   AttnBwdSmem* sm = reinterpret_cast<AttnBwdSmem*>(sDS + 2 * kPBytes);
+  uint8_t* sStat = sP;  // kT: stage s holds [-lse2 x 128 | -D' x 128] fp32 at +s*1024 (there is no sP tile)
 
   // dQ_i = dS K_j with A = dS read from TMEM (a bf16 copy written by the softmax warps into the 64 spare columns)
   // instead of from the K-major smem tile: -12 % shared-memory traffic per tile pair, at the price of a single-
   // buffered TMEM operand that must be free again before the next tile's first half is written.  With dropout the
   // softmax halves are long enough to hide that (7.9 -> 7.7 ms per launch); without dropout they are not (6.0 ->
   // 6.6 ms), so the variant is tied to the dropout instantiation.
-  constexpr bool kTsDq = kDrop;
+  constexpr bool kTsDq = kDrop && !kT;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -206,6 +292,8 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_init(&sm->ds_free[i], 1);
     }
     mbar_init(&sm->p_full, kSoftmaxWarps);
+    mbar_init(&sm->pt_full[0], kSoftmaxWarps);
+    mbar_init(&sm->pt_full[1], kSoftmaxWarps);
     mbar_init(&sm->p_free, 1);
     mbar_init(&sm->tds_free, 1);
     mbar_init(&sm->dq_full, 1);
@@ -242,10 +330,12 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const int qt = (i + jt) % nq;  // staggered start, see header
       mbar_wait_backoff(&sm->qdo_empty[st], (((uint32_t)i / kQStages) & 1u) ^ 1u);
       if (elect_one()) {
-        mbar_expect_tx(&sm->qdo_full[st], 2 * kTileBytesB);
+        mbar_expect_tx(&sm->qdo_full[st], 2 * kTileBytesB + (kT ? 1024 : 0));
         uint8_t* sQ = sQdO + st * 2 * kTileBytesB;
         tma_load_3d(sQ, &tm_qkv, &sm->qdo_full[st], h * kHdB, qt * kTileB, b);
         tma_load_3d(sQ + kTileBytesB, &tm_do, &sm->qdo_full[st], h * kHdB, qt * kTileB, b);
+        if (kT)
+          bulk_load(sStat + st * 1024, stat + (((long long)b * H + h) * nqt + qt) * 256, 1024, &sm->qdo_full[st]);
       }
       __syncwarp();
     }
@@ -277,9 +367,81 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       __syncwarp();
     };
+    // ---- transposed formulation (kT) ----
+    constexpr uint32_t idesc_a = umma_idesc_bf16(128, 64, 0, 1);  // dV, dK: A = P^T / dS^T in TMEM, B (dO_i / Q_i) MN-major
+    // S^T / dP^T for the queries [64 hf, 64 hf + 64): A = all 128 rows of K_j / V_j, B = rows [64 hf, ..) of Q_i / dO_i
+    auto issue_half_t = [&](int st, int hf) {
+      const uint32_t dQ = dQ0 + (uint32_t)st * (2 * kTileBytesB >> 4) + (uint32_t)hf * (kTileBytesB / 2 >> 4);
+      const uint32_t dDO = dQ + (kTileBytesB >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kHdB / 16; ++k)
+          umma_ss(tS + hf * 64, umma_desc(dK + 2 * k, kHi), umma_desc(dQ + 2 * k, kHi), idesc_h, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kHdB / 16; ++k)
+          umma_ss(tDP + hf * 64, umma_desc(dV + 2 * k, kHi), umma_desc(dDO + 2 * k, kHi), idesc_h, k > 0 ? 1u : 0u);
+        tc_commit(&sm->s_full[hf]);
+      }
+      __syncwarp();
+    };
+    // dV_j += P^T dO_i, dK_j += dS^T Q_i over the 64 queries of half hf: four k-steps of 16 queries whose bf16 A
+    // operands sit in place in the first 8 of the 16 S^T / dP^T columns they were computed from
+    auto issue_dvdk = [&](int st, int hf, uint32_t accum) {
+      const uint32_t dQm = (dQ0 + (uint32_t)st * (2 * kTileBytesB >> 4)) | kMn, dDOm = dQm + (kTileBytesB >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ts(tDV, tS + 16 * (hf * 4 + kk), umma_desc(dDOm + 128 * (hf * 4 + kk), kHi), idesc_a, kk > 0 ? 1u : accum);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ts(tDK, tDP + 16 * (hf * 4 + kk), umma_desc(dQm + 128 * (hf * 4 + kk), kHi), idesc_a, kk > 0 ? 1u : accum);
+      }
+      __syncwarp();
+    };
     mbar_wait(&sm->kv_full, 0);
     mbar_wait(&sm->qdo_full[0], 0);
     tc_fence_after();
+    if constexpr (kT) {
+      // Tensor-pipe order per tile: [dV_a dK_a | S^T_a' dP^T_a'] [dV_b dK_b | S^T_b' dP^T_b' | dQ]  (' = tile i+1).  The MMAs of
+      // one thread execute in issue order, so refilling a half's S^T / dP^T columns right behind the dV / dK MMAs that
+      // read P^T / dS^T from them needs no barrier.
+      issue_half_t(0, 0);
+      issue_half_t(0, 1);
+      int st = 0;
+      for (int i = 0; i < nq; ++i) {
+        const int stn = st + 1 == kQStages ? 0 : st + 1;
+        const bool more = i + 1 < nq;
+        mbar_wait(&sm->pt_full[0], (uint32_t)i & 1u);  // P^T / dS^T of the first 64 queries written
+        tc_fence_after();
+        issue_dvdk(st, 0, i > 0 ? 1u : 0u);
+        if (more) {
+          mbar_wait(&sm->qdo_full[stn], ((uint32_t)(i + 1) / kQStages) & 1u);
+          tc_fence_after();
+          issue_half_t(stn, 0);
+        }
+        mbar_wait(&sm->pt_full[1], (uint32_t)i & 1u);
+        tc_fence_after();
+        issue_dvdk(st, 1, 1u);
+        if (elect_one()) tc_commit(&sm->qdo_empty[st]);  // Q_i / dO_i / statistics of tile i are consumed
+        __syncwarp();
+        if (more) issue_half_t(stn, 1);
+        if (i > 0) {
+          mbar_wait(&sm->dq_free, (uint32_t)(i - 1) & 1u);  // drain warps have read dQ_{i-1}
+          tc_fence_after();
+        }
+        // dQ_i = dS K_j: A = the [kv rows][q contiguous] dS^T tile read MN-major (M = q), B = K_j MN-major
+        const uint32_t dDSm = (dDS0 + (uint32_t)(i & 1) * (kPBytes >> 4)) | kMn, dKm = dK | kMn;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kTileB / 16; ++k)
+            umma_ss(tDQ, umma_desc(dDSm + 128 * k, kHi), umma_desc(dKm + 128 * k, kHi), idesc_t, k > 0 ? 1u : 0u);
+          tc_commit(&sm->dq_full);
+          tc_commit(&sm->ds_free[i & 1]);
+        }
+        __syncwarp();
+        st = stn;
+      }
+    } else {
     issue_half(0, 0);
     issue_half(0, 1);
     int st = 0;
@@ -353,12 +515,88 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       st = stn;
     }
+    }
   } else if (warp < kSoftmaxWarps) {
     // ===== softmax warps: thread == query row (TMEM lane quarter warp % 4), 16 keys (warp / 4) of each key half =====
+    // (kT: thread == key row, 16 queries (warp / 4) of each query half)
     const int qd4 = warp & 3, chunk = warp >> 2;
     const int r = qd4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd4 * 32) << 16;
     const float c_log2 = scale * 1.4426950408889634f;
+    if constexpr (kT) {
+      // Dropout: lane L generates the keep bytes of (query q0 + (L & 15), key group L >> 4 of this warp's 32 key rows);
+      // a 16 x 16 byte transpose inside each half-warp then hands every lane the bytes of its own key row for the 16
+      // queries -- the masks stay exactly the forward kernel's (one Philox group = 16 consecutive keys of one query).
+      const unsigned long long bh_row0 = ((unsigned long long)b * H + h) * (unsigned long long)N;
+      const unsigned long long npad16 = (unsigned long long)(((N + 15) & ~15) >> 4);
+      const unsigned long long kgrp = (unsigned long long)((kv0 + qd4 * 32 + (lane >> 4) * 16) >> 4);
+      int st3 = 0, qt = jt % nq;
+      for (int i = 0; i < nq; ++i) {
+        const uint32_t aDSbuf = smem_u32(sDS) + (uint32_t)(i & 1) * kPBytes;
+        const uint32_t aStat = smem_u32(sStat) + (uint32_t)st3 * 1024u + (uint32_t)chunk * 64u;
+        mbar_wait(&sm->qdo_full[st3], ((uint32_t)i / kQStages) & 1u);  // column statistics of tile i (already landed)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {  // query halves
+          uint32_t sv[16], dp[16];
+          mbar_wait(&sm->s_full[hf], (uint32_t)i & 1u);
+          tc_fence_after();
+          tmem_ld16(tS + lane_off + hf * 64 + chunk * 16, sv);
+          tmem_ld16(tDP + lane_off + hf * 64 + chunk * 16, dp);
+          uint32_t mk[4] = {0, 0, 0, 0};
+          if (kDrop) {
+            const int ql = qt * kTileB + hf * 64 + chunk * 16 + (lane & 15);
+            const unsigned long long grp = (bh_row0 + (unsigned long long)(ql < N ? ql : 0)) * npad16 + kgrp;
+            drop_bits16(drop, grp, mk);
+            drop_keep_sign16(mk, drop_thr8(drop, grp));
+            transpose16x16_bytes(mk, lane);
+          }
+          tmem_ld_wait();
+          uint32_t pk[8], dk[8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {  // queries 4u .. 4u+3 of this thread's 16
+            const float4 nl = ld_shared_f4(aStat + (uint32_t)(hf * 256 + u * 16));        // -lse2 (+inf rows: -inf)
+            const float4 nd = ld_shared_f4(aStat + 512u + (uint32_t)(hf * 256 + u * 16));  // -D'
+            const float nls[4] = {nl.x, nl.y, nl.z, nl.w}, nds[4] = {nd.x, nd.y, nd.z, nd.w};
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              const int e = 4 * u + 2 * v, t = 2 * u + v;
+              const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), c_log2, nls[2 * v]));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c_log2, nls[2 * v + 1]));
+              const float a0 = fmaf(__uint_as_float(dp[e]), scale, nds[2 * v]);
+              const float a1 = fmaf(__uint_as_float(dp[e + 1]), scale, nds[2 * v + 1]);
+              if (kDrop) {
+                const uint32_t m = v ? prmt<0xBBAAu>(mk[u], 0u) : prmt<0x9988u>(mk[u], 0u);
+                const uint32_t kept = pack_bf16(p0 * a0, p1 * a1);
+                const uint32_t dropped = pack_bf16(p0 * nds[2 * v], p1 * nds[2 * v + 1]);
+                pk[t] = pack_bf16(p0, p1) & m;
+                dk[t] = (kept & m) | (dropped & ~m);
+              } else {
+                pk[t] = pack_bf16(p0, p1);
+                dk[t] = pack_bf16(p0 * a0, p1 * a1);
+              }
+            }
+          }
+          if (hf == 0 && i >= 2)
+            mbar_wait(&sm->ds_free[i & 1], (((uint32_t)i >> 1) - 1u) & 1u);  // dQ of tile i-2 has read this dS^T buffer
+          tmem_st8(tS + lane_off + hf * 64 + chunk * 16, pk);   // P^T, in place: A operand of dV
+          tmem_st8(tDP + lane_off + hf * 64 + chunk * 16, dk);  // dS^T, in place: A operand of dK
+          // key row r of 64-query block hf: 16-byte pieces chunk * 2 + g, XOR-swizzled with (r & 7)
+          const uint32_t row_off = (uint32_t)hf * 16384u + (uint32_t)r * 128u;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t piece = (uint32_t)((chunk * 2 + g) ^ (r & 7)) * 16u;
+            st_shared_v4(aDSbuf + row_off + piece, dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm->pt_full[hf]);
+        }
+        qt = (qt + 1 == nq) ? 0 : qt + 1;
+        st3 = st3 + 1 == kQStages ? 0 : st3 + 1;
+      }
+    } else {
     const float* lse_bh = lse + ((long long)b * H + h) * N;
     const float* dv_bh = dvec + ((long long)b * H + h) * N;
     const float log2_inv_keep = kDrop ? __log2f(drop.inv_keep) : 0.f, keep_prob = kDrop ? 1.0f / drop.inv_keep : 1.0f;
@@ -435,6 +673,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->p_full);
+    }
     }
     // ---- epilogue: dK_j, dV_j from TMEM -> bf16 rows of dqkv ----
     mbar_wait(&sm->ds_free[(nq - 1) & 1], ((uint32_t)(nq - 1) >> 1) & 1u);
@@ -595,13 +834,23 @@ static int make_tok_tmap(CUtensorMap* tm, const void* base, int B, int N, int co
   return make_tmap_bf16(tm, base, 3, dims, strides, box);
 }
 
-// workspace: Dvec [B,H,N] fp32 | dQ accumulator [B*H][nq][16][128][4] fp32
+// workspace: Dvec [B,H,N] fp32 | dQ accumulator [B*H][nq][16][128][4] fp32 | column statistics [B*H][nq][256] fp32
 static size_t ws_dvec_bytes(int B, int N, int H) { return (((size_t)B * H * N * 4) + 255) & ~(size_t)255; }
+static size_t ws_dq_bytes(int B, int N, int H) {
+  return (size_t)B * H * ((N + kTileB - 1) / kTileB) * 16 * 128 * 4 * sizeof(float);
+}
+static size_t ws_stat_bytes(int B, int N, int H) { return (size_t)B * H * ((N + kTileB - 1) / kTileB) * 256 * sizeof(float); }
 
 size_t tc_attn_bwd_workspace(int B, int N, int H, int hd) {
   (void)hd;
-  const size_t nq = (N + kTileB - 1) / kTileB;
-  return ws_dvec_bytes(B, N, H) + (size_t)B * H * nq * 16 * 128 * 4 * sizeof(float);
+  return ws_dvec_bytes(B, N, H) + ws_dq_bytes(B, N, H) + ws_stat_bytes(B, N, H);
+}
+
+// Which instantiations use the transposed formulation: TVIT_ATTN_BWD_T bit 0 = without dropout, bit 1 = with dropout
+// (A-B timing; the default is what measured faster on B200).
+static int attn_bwd_t_mask() {
+  static const int m = [] { const char* e = getenv("TVIT_ATTN_BWD_T"); return e ? atoi(e) : TVIT_ATTN_BWD_T_DEFAULT; }();
+  return m;
 }
 
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* ws,
@@ -615,12 +864,15 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   const int nq = (N + kTileB - 1) / kTileB;
   float* dvec = reinterpret_cast<float*>(ws);
   float* dqacc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + ws_dvec_bytes(B, N, H));
-  const size_t dq_bytes = (size_t)B * H * nq * 16 * 128 * 4 * sizeof(float);
+  const size_t dq_bytes = ws_dq_bytes(B, N, H);
+  float* stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + ws_dvec_bytes(B, N, H) + dq_bytes);
 
   constexpr int smem_bytes = 2 * kTileBytesB + kQStages * 2 * kTileBytesB + 3 * kPBytes + 1024 + 1280;  // 226.25 KB
   int rc;
-  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false>, smem_bytes)) != TVIT_OK) return rc;
-  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false, false>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true, false>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false, true>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true, true>, smem_bytes)) != TVIT_OK) return rc;
 
   TVIT_CUDA_OK(cudaMemsetAsync(dqacc, 0, dq_bytes, s));
   {
@@ -639,10 +891,24 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   if (const char* e = getenv("TVIT_ATTN_TAIL_DBG")) tail |= atoi(e) << 8;
   const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv;
   const __nv_bfloat16* dop = (const __nv_bfloat16*)dout;
-  if (dc.thr16 != 0)
-    tc_attn_bwd_kernel<true><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, qp, dop, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, N, tail, H, scale, dc);
-  else
-    tc_attn_bwd_kernel<false><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, qp, dop, lse, dvec, dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, N, tail, H, scale, dc);
+  const bool drop_on = dc.thr16 != 0;
+  const bool transposed = (attn_bwd_t_mask() >> (drop_on ? 1 : 0)) & 1;
+  if (transposed) {
+    const long long total = (long long)B * H * nq * kTileB;
+    attn_bwd_stat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        lse, dvec, stat, B * H, N, nq, drop_on ? log2f(dc.inv_keep) : 0.f, scale / dc.inv_keep);
+    TVIT_LAUNCH_OK();
+  }
+#define TVIT_BWD_LAUNCH(DROP, T)                                                                                      \
+  tc_attn_bwd_kernel<DROP, T><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, qp, dop, lse, dvec, stat, dqacc, \
+                                                                        (__nv_bfloat16*)dqkv, dqkv_colsum, N, tail, H, \
+                                                                        scale, dc)
+  if (drop_on) {
+    if (transposed) TVIT_BWD_LAUNCH(true, true); else TVIT_BWD_LAUNCH(true, false);
+  } else {
+    if (transposed) TVIT_BWD_LAUNCH(false, true); else TVIT_BWD_LAUNCH(false, false);
+  }
+#undef TVIT_BWD_LAUNCH
   TVIT_LAUNCH_OK();
   {
     const long long total = (long long)B * H * nq * 4 * 128;
