@@ -135,6 +135,11 @@ size_t tvit_attn_bwd_workspace_bytes(int engine, int dtype, int B, int N, int H,
 int tvit_attn_bwd(int engine, int dtype, const void* qkv, const void* out, const void* dout, const float* lse,
                   void* dqkv, void* workspace, size_t workspace_bytes, int B, int N, int H, int hd,
                   const tvit_dropout* drop, float* dqkv_colsum, tvit_stream_t stream);
+/* Formulation of the tcgen05 attention backward kernel (bit 0 / 1: transposed form without / with dropout; bit 2 / 3:
+ * whole-tile S / dP MMAs with two issuing warps without / with dropout; 0 = key-half pipelined, the default).  All
+ * variants compute the same function with the same dropout masks; the switch exists for A-B timing and for the parity
+ * tests, which run every variant.  Sets the mask unless mask < 0 and returns the previous one. */
+int tvit_attn_bwd_variant(int mask);
 /* probs[b,h,q,k] = softmax(q k^T * hd^-0.5) materialised (interpretability API, model.py:325-350) */
 int tvit_attn_probs(int dtype, const void* qkv, float* probs, int B, int N, int H, int hd, tvit_stream_t stream);
 

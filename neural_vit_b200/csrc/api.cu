@@ -43,6 +43,7 @@ int attn_probs(int dtype, const void* qkv, float* probs, int B, int N, int H, in
 int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, const tvit_dropout* drop,
                 cudaStream_t s);
 size_t tc_attn_bwd_workspace(int B, int N, int H, int hd);
+int tc_attn_bwd_variant(int mask);
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* ws,
                 size_t ws_bytes, int B, int N, int H, int hd, const tvit_dropout* drop, float* dqkv_colsum,
                 cudaStream_t s);
@@ -133,6 +134,8 @@ extern "C" int tvit_attn_bwd(int engine, int dtype, const void* qkv, const void*
   }
   return fail(TVIT_ERR_BAD_ARG, "attn_bwd: unknown engine %d", engine);
 }
+
+extern "C" int tvit_attn_bwd_variant(int mask) { return tc_attn_bwd_variant(mask); }
 
 extern "C" int tvit_attn_probs(int dtype, const void* qkv, float* probs, int B, int N, int H, int hd,
                                tvit_stream_t stream) {

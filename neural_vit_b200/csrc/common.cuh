@@ -151,6 +151,12 @@ __device__ __forceinline__ f32x2 pk2(float lo, float hi) {
 __device__ __forceinline__ void up2(f32x2 v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
+__device__ __forceinline__ uint32_t pack_bf16_2(f32x2 v) {  // bf16x2 of an fp32 pair (lo -> low half)
+  float lo, hi;
+  up2(v, lo, hi);
+  return pack_bf16(lo, hi);
+}
+#ifndef TVIT_SCALAR_F32X2  // A-B builds only: -DTVIT_SCALAR_F32X2 emits the scalar instructions instead
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
@@ -166,6 +172,23 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+#else
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  float a0, a1, b0, b1, c0, c1;
+  up2(a, a0, a1); up2(b, b0, b1); up2(c, c0, c1);
+  return pk2(fmaf(a0, b0, c0), fmaf(a1, b1, c1));
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  float a0, a1, b0, b1;
+  up2(a, a0, a1); up2(b, b0, b1);
+  return pk2(a0 * b0, a1 * b1);
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  float a0, a1, b0, b1;
+  up2(a, a0, a1); up2(b, b0, b1);
+  return pk2(a0 + b0, a1 + b1);
+}
+#endif
 // gelu_fast / gelu_grad_fast of two values at once (same polynomial), both scaled by k (the dropout 1/(1-p)):
 // y = k x Phi(x);  d = k (Phi(x) + x pdf(x)) (only when kGrad).
 template <bool kGrad, bool kScale>

@@ -239,7 +239,8 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
       }
       // ---- pass B: exponentials, partial row sum (of the un-dropped probabilities), dropout mask, bf16 pack ----
       // (the 1/(1-p) factor of kept elements is applied once to O in the epilogue)
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      f32x2 rs01 = pk2(0.f, 0.f), rs23 = rs01;
+      const f32x2 sl2 = pk2(scale_log2, scale_log2), nm2 = pk2(-m_new, -m_new);
       const unsigned long long g0 = (rowe + (unsigned long long)j * kTile + hf * 64) >> 4;  // 16-element groups
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
@@ -267,12 +268,14 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int c = g * 16 + u * 4;
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c]), scale_log2, -m_new));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c + 1]), scale_log2, -m_new));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(sv[c + 2]), scale_log2, -m_new));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(sv[c + 3]), scale_log2, -m_new));
-            rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-            uint32_t v01 = pack_bf16(p0, p1), v23 = pack_bf16(p2, p3);
+            // packed fp32x2 (FFMA2 / FADD2; bit-identical per lane to the scalar form): exponent arguments, row sums
+            float e0, e1, e2, e3;
+            up2(fma2(pk2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), e0, e1);
+            up2(fma2(pk2(__uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3])), sl2, nm2), e2, e3);
+            const f32x2 p01 = pk2(ex2_approx(e0), ex2_approx(e1)), p23 = pk2(ex2_approx(e2), ex2_approx(e3));
+            rs01 = add2(rs01, p01);
+            rs23 = add2(rs23, p23);
+            uint32_t v01 = pack_bf16_2(p01), v23 = pack_bf16_2(p23);
             if (kDrop) {
               v01 &= drop_keep_mask2<0>(w[u], tg2);
               v23 &= drop_keep_mask2<1>(w[u], tg2);
@@ -283,6 +286,9 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
         }
         tmem_st16(tP + lane_off + hf * 32 + c2 * 16, pk);
       }
+      float rs0, rs1, rs2, rs3;
+      up2(rs01, rs0, rs1);
+      up2(rs23, rs2, rs3);
       l = l * corr + ((rs0 + rs1) + (rs2 + rs3));
       m2 = m_new;
       tmem_st_wait();

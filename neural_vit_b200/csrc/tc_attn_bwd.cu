@@ -36,6 +36,9 @@
 
 namespace tvit {
 
+#ifndef TVIT_ATTN_BWD_TSDQ
+#define TVIT_ATTN_BWD_TSDQ 1  // 0: dQ reads dS from shared memory in the dropout instantiation too (A-B builds)
+#endif
 #ifndef TVIT_ATTN_BWD_T_DEFAULT
 #define TVIT_ATTN_BWD_T_DEFAULT 0
 #endif
@@ -148,6 +151,19 @@ __device__ __forceinline__ void transpose16x16_bytes(uint32_t (&w)[4], int lane)
   }
 }
 
+// Optional event trace (-DTVIT_ATTN_TRACE builds only; development aid): CTA (0,0,0) records clock64 at pipeline events,
+// g_attn_trace[(slot * 32 + tile) * 8 + event]; read back with tvit_attn_bwd_trace().
+#ifdef TVIT_ATTN_TRACE
+__device__ long long g_attn_trace[8 * 32 * 8];
+#define TVIT_TRACE(slot, tile, ev)                                                                   \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 && (tile) < 32) \
+      g_attn_trace[((slot) * 32 + (tile)) * 8 + (ev)] = clock64();                                   \
+  } while (0)
+#else
+#define TVIT_TRACE(slot, tile, ev) do { } while (0)
+#endif
+
 constexpr int kQStages = 3;  // Q / dO tiles in flight
 struct AttnBwdSmem {
   uint64_t kv_full, qdo_full[kQStages], qdo_empty[kQStages], s_full[2], s_free[2], p_full, p_free, ds_free[2], dq_full,
@@ -158,51 +174,45 @@ struct AttnBwdSmem {
 };
 static_assert(sizeof(AttnBwdSmem) <= 1280, "AttnBwdSmem must fit the 1.25 KB tail of the dynamic smem block");
 
-// Dvec[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
+// Dvec[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d], and the per-query statistics in the form the main kernel consumes: one
+// 1 KB record per (b, h, query tile), [-lse2 x 128 | -D' x 128] with lse2 = lse log2(e) - log2(1/(1-p)) and
+// D' = D scale (1-p); rows past N get -inf / 0 so that their P is exactly 0.  One thread per (b, padded q, h).
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
-                                     float* __restrict__ dvec, int B, int N, int H) {
+                                     const float* __restrict__ lse, float* __restrict__ dvec, float* __restrict__ stat,
+                                     int B, int N, int H, int nqt, float log2_inv_keep, float d_scale) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long total = (long long)B * N * H;
+  const int npadq = nqt * kTileB;
+  const long long total = (long long)B * npadq * H;
   if (idx >= total) return;
   const int h = (int)(idx % H);
-  const long long row = idx / H;  // b*N + q
-  const int b = (int)(row / N), q = (int)(row % N);
-  const __nv_bfloat16* po = o + row * (long long)(H * kHdB) + h * kHdB;
-  const __nv_bfloat16* pd = dout + row * (long long)(H * kHdB) + h * kHdB;
-  float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < kHdB / 8; ++c) {
-    const uint4 a = *reinterpret_cast<const uint4*>(po + 8 * c);
-    const uint4 d = *reinterpret_cast<const uint4*>(pd + 8 * c);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[t]));
-      const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[t]));
-      s += fa.x * fd.x + fa.y * fd.y;
-    }
-  }
-  dvec[((long long)b * H + h) * N + q] = s;
-}
-
-// Column statistics of the transposed kernel, one 1 KB record per (b, h, query tile): [-lse2 x 128 | -D' x 128] with
-// lse2 = lse log2(e) - log2(1/(1-p)) and D' = D scale (1-p); rows past N get -inf / 0 so that their P is exactly 0.
-__global__ void attn_bwd_stat_kernel(const float* __restrict__ lse, const float* __restrict__ dvec,
-                                     float* __restrict__ stat, int BH, int N, int nqt, float log2_inv_keep,
-                                     float d_scale) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= (long long)BH * nqt * kTileB) return;
-  const int r = (int)(idx & (kTileB - 1));
-  const long long t = idx >> 7;  // bh * nqt + tile
-  const int q = (int)(t % nqt) * kTileB + r;
-  const long long bh = t / nqt;
+  const long long prow = idx / H;  // b * npadq + q
+  const int b = (int)(prow / npadq), q = (int)(prow % npadq);
   float nl = -INFINITY, nd = 0.f;
   if (q < N) {
-    nl = log2_inv_keep - lse[bh * N + q] * 1.4426950408889634f;
-    nd = -dvec[bh * N + q] * d_scale;
+    const long long row = (long long)b * N + q;
+    const __nv_bfloat16* po = o + row * (long long)(H * kHdB) + h * kHdB;
+    const __nv_bfloat16* pd = dout + row * (long long)(H * kHdB) + h * kHdB;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kHdB / 8; ++c) {
+      const uint4 a = *reinterpret_cast<const uint4*>(po + 8 * c);
+      const uint4 d = *reinterpret_cast<const uint4*>(pd + 8 * c);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[t]));
+        const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[t]));
+        s += fa.x * fd.x + fa.y * fd.y;
+      }
+    }
+    const long long bhq = ((long long)b * H + h) * N + q;
+    dvec[bhq] = s;
+    nl = log2_inv_keep - lse[bhq] * 1.4426950408889634f;
+    nd = -s * d_scale;
   }
-  stat[t * 256 + r] = nl;
-  stat[t * 256 + 128 + r] = nd;
+  float* rec = stat + (((long long)b * H + h) * nqt + (q >> 7)) * 256 + (q & (kTileB - 1));
+  rec[0] = nl;
+  rec[128] = nd;
 }
 
 // dq accumulator layout: [(b*H+h)][q tile][16 chunks][128 rows][4 fp32]
@@ -246,8 +256,11 @@ __global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_
 // kT selects the transposed formulation (see the header): S^T = K_j Q_i^T and dP^T = V_j dO_i^T land in TMEM with
 // thread == key row, so that P^T and dS^T -- written back in place as bf16 -- are the TMEM A operands of the dV / dK
 // MMAs, and only dS^T goes through shared memory (for dQ).  `stat` holds the per-query column statistics
-// [(b,h)][q tile][-lse2 x 128 | -D' x 128] produced by attn_bwd_stat_kernel (kT only).
-template <bool kDrop, bool kT>
+// [(b,h)][q tile][-lse2 x 128 | -D' x 128] produced by attn_bwd_prep_kernel.
+// kFull (non-transposed only): S and dP are issued as whole N = 128 MMAs (4 x 107 clk instead of 8 x 75 clk,
+// profiles/r2_mma_rate.txt) into the single-buffered S / dP columns as soon as every softmax warp has loaded tile i's
+// scores -- i.e. half-way through the softmax of tile i -- instead of half by half, and dQ always takes dS from TMEM.
+template <bool kDrop, bool kT, bool kFull>
 __global__ void __launch_bounds__(kAttnBwdThreads, 1)
 tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
@@ -269,7 +282,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   // buffered TMEM operand that must be free again before the next tile's first half is written.  With dropout the
   // softmax halves are long enough to hide that (7.9 -> 7.7 ms per launch); without dropout they are not (6.0 ->
   // 6.6 ms), so the variant is tied to the dropout instantiation.
-  constexpr bool kTsDq = kDrop && !kT;
+  constexpr bool kTsDq = ((kDrop && TVIT_ATTN_BWD_TSDQ) || kFull) && !kT;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -298,7 +311,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_init(&sm->tds_free, 1);
     mbar_init(&sm->dq_full, 1);
     mbar_init(&sm->dq_free, 128);
-    mbar_init(&sm->tail_ready, 64);
+    mbar_init(&sm->tail_ready, kFull ? 32 : 64);
     fence_barrier_init();
   }
   if (warp == 21) {
@@ -442,6 +455,54 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         st = stn;
       }
     } else {
+    constexpr uint32_t idesc_f = umma_idesc_bf16(128, 128, 0, 0);  // S, dP whole tiles (kFull)
+    auto issue_full = [&](int st) {
+      const uint32_t dQ = dQ0 + (uint32_t)st * (2 * kTileBytesB >> 4), dDO = dQ + (kTileBytesB >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kHdB / 16; ++k)
+          umma_ss(tS, umma_desc(dQ + 2 * k, kHi), umma_desc(dK + 2 * k, kHi), idesc_f, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kHdB / 16; ++k)
+          umma_ss(tDP, umma_desc(dDO + 2 * k, kHi), umma_desc(dV + 2 * k, kHi), idesc_f, k > 0 ? 1u : 0u);
+        tc_commit(&sm->s_full[0]);
+        tc_commit(&sm->s_full[1]);
+      }
+      __syncwarp();
+    };
+    if constexpr (kFull) {
+      // MMA issue is split over two warps (on different schedulers): measured with the event trace, the issuing warp --
+      // which shares its scheduler with four busy softmax warps -- needs ~70 clk per tcgen05.mma, i.e. ~2800 clk per
+      // tile pair for 40 MMAs: as long as the tensor pipe itself.  This warp issues S / dP of the next tile and dQ;
+      // warp 22 issues dV and dK (below).
+      issue_full(0);
+      int st = 0;
+      for (int i = 0; i < nq; ++i) {
+        const int stn = st + 1 == kQStages ? 0 : st + 1;
+        if (i + 1 < nq) {  // refill S / dP as soon as every softmax warp holds tile i's second half in registers
+          mbar_wait(&sm->qdo_full[stn], ((uint32_t)(i + 1) / kQStages) & 1u);
+          mbar_wait(&sm->s_free[1], (uint32_t)i & 1u);
+          tc_fence_after();
+          TVIT_TRACE(0, i, 0);
+          issue_full(stn);
+        }
+        mbar_wait(&sm->p_full, (uint32_t)i & 1u);  // P / dS of tile i written (smem + the TMEM copy of dS)
+        if (i > 0) mbar_wait(&sm->dq_free, (uint32_t)(i - 1) & 1u);  // drain warps have read dQ_{i-1}
+        tc_fence_after();
+        TVIT_TRACE(0, i, 1);
+        const uint32_t dKm = dK | kMn;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kTileB / 16; ++k)
+            umma_ts(tDQ, tDS + k * 8, umma_desc(dKm + 128 * k, kHi), idesc_q, k > 0 ? 1u : 0u);
+          tc_commit(&sm->dq_full);
+          tc_commit(&sm->tds_free);
+        }
+        __syncwarp();
+        TVIT_TRACE(0, i, 2);
+        st = stn;
+      }
+    } else {
     issue_half(0, 0);
     issue_half(0, 1);
     int st = 0;
@@ -456,6 +517,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       mbar_wait(&sm->p_full, (uint32_t)i & 1u);  // sP / sDS written for tile i
       tc_fence_after();
+      TVIT_TRACE(0, i, 1);
       // MN-major operands (LBO 16384): Q_i, dO_i as B; sP, sDS as A.  K-major sDS as A of the dQ MMA.
       const uint32_t dQm = (dQ0 + (uint32_t)st * (2 * kTileBytesB >> 4)) | kMn, dDOm = dQm + (kTileBytesB >> 4);
       const uint32_t dDS = dDS0 + (uint32_t)(i & 1) * (kPBytes >> 4), dDSm = dDS | kMn, dKm = dK | kMn;
@@ -473,6 +535,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           mbar_wait(&sm->dq_free, (uint32_t)(i - 1) & 1u);  // drain warps have read dQ_{i-1}
           tc_fence_after();
         }
+        TVIT_TRACE(0, i, 2);
         if (elect_one()) {
           // reduction over the 128 keys, B = K_j MN-major; A = dS from TMEM (8 columns per 16 keys) or from the
           // K-major smem tile (two 64-key blocks 16 KB apart)
@@ -516,6 +579,41 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       st = stn;
     }
     }
+    }
+  } else if (kFull && warp == 22) {
+    // ============================ second MMA issuer (kFull): dV_j += P^T dO_i, dK_j += dS^T Q_i ============================
+    constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);
+    constexpr uint32_t kHi = umma_desc_hi(1024);
+    constexpr uint32_t kMn = (16384u >> 4) << 16;
+    const uint32_t dQ0 = umma_desc_lo(smem_u32(sQdO), 0), dP = umma_desc_lo(smem_u32(sP), 0) | kMn;
+    const uint32_t dDS0 = umma_desc_lo(smem_u32(sDS), 0);
+    int st = 0;
+    for (int i = 0; i < nq; ++i) {
+      mbar_wait(&sm->p_full, (uint32_t)i & 1u);
+      tc_fence_after();
+      TVIT_TRACE(4, i, 0);
+      const uint32_t dQm = (dQ0 + (uint32_t)st * (2 * kTileBytesB >> 4)) | kMn, dDOm = dQm + (kTileBytesB >> 4);
+      const uint32_t dDSm = (dDS0 + (uint32_t)(i & 1) * (kPBytes >> 4)) | kMn;
+      const uint32_t accum = i > 0 ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kTileB / 16; ++k)
+          umma_ss(tDV, umma_desc(dP + 128 * k, kHi), umma_desc(dDOm + 128 * k, kHi), idesc_t, k > 0 ? 1u : accum);
+        tc_commit(&sm->p_free);  // sP may be overwritten by tile i+1
+      }
+      __syncwarp();
+      TVIT_TRACE(4, i, 1);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kTileB / 16; ++k)
+          umma_ss(tDK, umma_desc(dDSm + 128 * k, kHi), umma_desc(dQm + 128 * k, kHi), idesc_t, k > 0 ? 1u : accum);
+        tc_commit(&sm->qdo_empty[st]);
+        tc_commit(&sm->ds_free[i & 1]);
+      }
+      __syncwarp();
+      TVIT_TRACE(4, i, 2);
+      st = st + 1 == kQStages ? 0 : st + 1;
+    }
   } else if (warp < kSoftmaxWarps) {
     // ===== softmax warps: thread == query row (TMEM lane quarter warp % 4), 16 keys (warp / 4) of each key half =====
     // (kT: thread == key row, 16 queries (warp / 4) of each query half)
@@ -523,6 +621,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const int r = qd4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd4 * 32) << 16;
     const float c_log2 = scale * 1.4426950408889634f;
+    const f32x2 c_log2_2 = pk2(c_log2, c_log2), scale_2 = pk2(scale, scale);
     if constexpr (kT) {
       // Dropout: lane L generates the keep bytes of (query q0 + (L & 15), key group L >> 4 of this warp's 32 key rows);
       // a 16 x 16 byte transpose inside each half-warp then hands every lane the bytes of its own key row for the 16
@@ -560,19 +659,19 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
               const int e = 4 * u + 2 * v, t = 2 * u + v;
-              const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), c_log2, nls[2 * v]));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), c_log2, nls[2 * v + 1]));
-              const float a0 = fmaf(__uint_as_float(dp[e]), scale, nds[2 * v]);
-              const float a1 = fmaf(__uint_as_float(dp[e + 1]), scale, nds[2 * v + 1]);
+              float e0, e1;
+              const f32x2 nl2 = pk2(nls[2 * v], nls[2 * v + 1]), nd2 = pk2(nds[2 * v], nds[2 * v + 1]);
+              up2(fma2(pk2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c_log2_2, nl2), e0, e1);
+              const f32x2 p = pk2(ex2_approx(e0), ex2_approx(e1));
+              const f32x2 a = fma2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), scale_2, nd2);
               if (kDrop) {
                 const uint32_t m = v ? prmt<0xBBAAu>(mk[u], 0u) : prmt<0x9988u>(mk[u], 0u);
-                const uint32_t kept = pack_bf16(p0 * a0, p1 * a1);
-                const uint32_t dropped = pack_bf16(p0 * nds[2 * v], p1 * nds[2 * v + 1]);
-                pk[t] = pack_bf16(p0, p1) & m;
+                const uint32_t kept = pack_bf16_2(mul2(p, a)), dropped = pack_bf16_2(mul2(p, nd2));
+                pk[t] = pack_bf16_2(p) & m;
                 dk[t] = (kept & m) | (dropped & ~m);
               } else {
-                pk[t] = pack_bf16(p0, p1);
-                dk[t] = pack_bf16(p0 * a0, p1 * a1);
+                pk[t] = pack_bf16_2(p);
+                dk[t] = pack_bf16_2(mul2(p, a));
               }
             }
           }
@@ -597,66 +696,78 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         st3 = st3 + 1 == kQStages ? 0 : st3 + 1;
       }
     } else {
-    const float* lse_bh = lse + ((long long)b * H + h) * N;
-    const float* dv_bh = dvec + ((long long)b * H + h) * N;
-    const float log2_inv_keep = kDrop ? __log2f(drop.inv_keep) : 0.f, keep_prob = kDrop ? 1.0f / drop.inv_keep : 1.0f;
+    // Per-query statistics (-lse2, -D') come ready-made from the prep kernel's records; with dropout (keep mask k,
+    // m = k / (1-p)): P m = P' k and dS = P (m dP scale - D scale) = P' (k dP scale - D'), where P' = P / (1-p) comes
+    // for free from the exponent (lse2 = lse log2(e) - log2(1/(1-p))) and D' = D scale (1-p).  Rows past N: -inf / 0.
+    const float* stat_row = stat + ((long long)b * H + h) * nqt * 256 + r;
     int qt = jt % nq;
-    float lse_next = (qt * kTileB + r < N) ? lse_bh[qt * kTileB + r] : INFINITY;
-    float d_next = (qt * kTileB + r < N) ? dv_bh[qt * kTileB + r] : 0.f;
+    float nl_next = stat_row[qt * 256], nd_next = stat_row[qt * 256 + 128];
+    // Dropout group (16 consecutive keys of one query row) of this thread's keys: a CTA-uniform 64-bit base plus a
+    // 32-bit row term (q * npad / 16 < 2^32 for every N this kernel accepts)
+    const uint32_t npad16 = (uint32_t)((N + 15) >> 4);
+    const unsigned long long grp_cta = (attn_drop_row_base(b, H, h, N, 0) + (unsigned long long)kv0) >> 4;
     for (int i = 0; i < nq; ++i) {
-      const int q = qt * kTileB + r;
-      // With dropout (keep mask k, m = k / (1-p)): P m = P' k and dS = P (m dP scale - D scale) = P' (k dP scale - D'),
-      // where P' = P / (1-p) comes for free from the exponent and D' = D scale (1-p).
-      const float lse2 = lse_next * 1.4426950408889634f - log2_inv_keep;  // +inf for rows past N -> P = 0
-      const float negDq = -d_next * scale * keep_prob;
+      const float nlse2 = nl_next, negDq = nd_next;
+      const f32x2 nlse2_2 = pk2(nlse2, nlse2), negDq_2 = pk2(negDq, negDq);
+      const unsigned long long grp_row = grp_cta + (unsigned long long)((uint32_t)(qt * kTileB + r) * npad16);
       {  // prefetch the next tile's row statistics so the global-load latency is off the critical path
         qt = (qt + 1 == nq) ? 0 : qt + 1;
-        const int qn = qt * kTileB + r;
-        lse_next = (qn < N) ? lse_bh[qn] : INFINITY;
-        d_next = (qn < N) ? dv_bh[qn] : 0.f;
+        nl_next = stat_row[qt * 256];
+        nd_next = stat_row[qt * 256 + 128];
       }
       const uint32_t aDSbuf = smem_u32(sDS) + (uint32_t)(i & 1) * kPBytes;
-      const unsigned long long rowe = attn_drop_row_base(b, H, h, N, q < N ? q : 0) + (unsigned long long)kv0;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {  // key halves; 16 keys per thread per half keep the live register set small
         uint32_t sv[16], dp[16];
         mbar_wait(&sm->s_full[hf], (uint32_t)i & 1u);
         tc_fence_after();
+        TVIT_TRACE(1 + (warp == 15), i, hf * 4 + 0);
         tmem_ld16(tS + lane_off + hf * 64 + chunk * 16, sv);
         tmem_ld16(tDP + lane_off + hf * 64 + chunk * 16, dp);
         tmem_ld_wait();
+        TVIT_TRACE(1 + (warp == 15), i, hf * 4 + 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm->s_free[hf]);  // this half's S / dP columns may be refilled
         uint32_t pk[8], dk[8];
         uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0;
         if (kDrop) {  // this thread's 16 keys are exactly one Philox group (common.cuh)
-          const unsigned long long grp = (rowe >> 4) + (unsigned long long)(hf * 4 + chunk);
+          const unsigned long long grp = grp_row + (unsigned long long)(hf * 4 + chunk);
           drop_bits16(drop, grp, w);
           tg2 = drop_tgc(drop_thr8(drop, grp));
         }
+        // packed fp32x2 arithmetic (FFMA2 / FMUL2: two IEEE operations per issue slot, bit-identical per lane to the
+        // scalar form): the TMEM loads deliver each element pair in an aligned register pair
 #pragma unroll
         for (int t = 0; t < 8; ++t) {  // element pairs (2t, 2t+1)
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * t]), c_log2, -lse2));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * t + 1]), c_log2, -lse2));
-          const float a0 = fmaf(__uint_as_float(dp[2 * t]), scale, negDq);
-          const float a1 = fmaf(__uint_as_float(dp[2 * t + 1]), scale, negDq);
+          float e0, e1;
+          up2(fma2(pk2(__uint_as_float(sv[2 * t]), __uint_as_float(sv[2 * t + 1])), c_log2_2, nlse2_2), e0, e1);
+          const f32x2 p = pk2(ex2_approx(e0), ex2_approx(e1));
+          const f32x2 a = fma2(pk2(__uint_as_float(dp[2 * t]), __uint_as_float(dp[2 * t + 1])), scale_2, negDq_2);
           if (kDrop) {
             const uint32_t m = (t & 1) ? drop_keep_mask2<1>(w[t >> 1], tg2) : drop_keep_mask2<0>(w[t >> 1], tg2);
-            const uint32_t kept = pack_bf16(p0 * a0, p1 * a1), dropped = pack_bf16(p0 * negDq, p1 * negDq);
-            pk[t] = pack_bf16(p0, p1) & m;
+            const uint32_t kept = pack_bf16_2(mul2(p, a)), dropped = pack_bf16_2(mul2(p, negDq_2));
+            pk[t] = pack_bf16_2(p) & m;
             dk[t] = (kept & m) | (dropped & ~m);
           } else {
-            pk[t] = pack_bf16(p0, p1);
-            dk[t] = pack_bf16(p0 * a0, p1 * a1);
+            pk[t] = pack_bf16_2(p);
+            dk[t] = pack_bf16_2(mul2(p, a));
           }
         }
+        TVIT_TRACE(1 + (warp == 15), i, hf * 4 + 2);
         if (hf == 0) {
+          // One wait covers all three operand buffers.  A tcgen05.commit completes when ALL earlier MMAs of the issuing
+          // thread have, and that thread issues dK_{i-2} (last reader of this sDS buffer) before dV_{i-1} (sP) before,
+          // with the TMEM dS operand, dQ_{i-1} (tDS): the latest of the commits implies the others.  Each extra wait
+          // on an already completed barrier cost ~130 clk here (a shared-memory round trip behind the UMMA operand
+          // traffic), ~300 clk per tile pair.  With two issuing warps (kFull) dV / dK and dQ are committed separately.
           if (kTsDq && i >= 1) mbar_wait(&sm->tds_free, (uint32_t)(i - 1) & 1u);  // dQ_{i-1} has read tDS
-          if (i >= 1) mbar_wait(&sm->p_free, (uint32_t)(i - 1) & 1u);  // dV_{i-1} has read sP
-          if (i >= 2) mbar_wait(&sm->ds_free[i & 1], (((uint32_t)i >> 1) - 1u) & 1u);  // tile i-2 has read this sDS
+          if ((!kTsDq || kFull) && i >= 1) mbar_wait(&sm->p_free, (uint32_t)(i - 1) & 1u);  // dV_{i-1} has read sP
         }
+        // (Deferring half a's TMEM store to the end of the tile, where the tensor pipe is idle and a tcgen05.st does not
+        // stall for 300-800 clk, lengthens the p_full -> dV -> dQ chain instead: 7.25 -> 7.56 ms.  Not kept.)
         if (kTsDq) tmem_st8(tDS + lane_off + hf * 32 + chunk * 8, dk);  // dS for the dQ MMA (A operand from TMEM)
+        TVIT_TRACE(1 + (warp == 15), i, hf * 4 + 3);
         // row r of 64-key block hf: 16-byte pieces chunk * 2 + g, XOR-swizzled with (r & 7)
         const uint32_t row_off = (uint32_t)hf * 16384u + (uint32_t)r * 128u;
 #pragma unroll
@@ -665,6 +776,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           st_shared_v4(smem_u32(sP) + row_off + piece, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           st_shared_v4(aDSbuf + row_off + piece, dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
         }
+        if (warp == 0) TVIT_TRACE(5 + hf, i, hf == 0 ? 5 : 1);
       }
       if (kTsDq) {
         tmem_st_wait();
@@ -731,6 +843,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     for (int i = 0; i < nq; ++i) {
       mbar_wait_backoff(&sm->dq_full, (uint32_t)i & 1u);
       tc_fence_after();
+      TVIT_TRACE(3, i, 0);
       float* tile = acc_bh + (long long)((i + jt) % nq) * (16 * 128 * 4) + r * 4;
 #pragma unroll 1
       for (int hc = 0; hc < 2; ++hc) {  // 32 columns at a time: this warpgroup runs with 64 registers
@@ -740,6 +853,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (hc == 1) {
           tc_fence_before();
           mbar_arrive(&sm->dq_free);
+          TVIT_TRACE(3, i, 1);
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -748,6 +862,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                                 __uint_as_float(o[4 * c + 3])));
         }
       }
+      TVIT_TRACE(3, i, 2);
     }
   } else if (warp >= 22) {
     // ============================ tail-query warps (22-23; see header) ============================
@@ -761,10 +876,11 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const __nv_bfloat16* dorow = dout + ((long long)b * N + qi) * D + h * kHdB;
       const float lse_t = lse[((long long)b * H + h) * N + qi], d_t = dvec[((long long)b * H + h) * N + qi];
       mbar_wait(&sm->kv_full, 0);
-      float dsr[2];
+      constexpr int kTailRows = kFull ? 4 : 2;  // kFull: warp 22 issues MMAs, warp 23 takes all 128 key rows
+      float dsr[kTailRows];
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int r = (warp - 22) * 32 + lane + 64 * rr, kv = kv0 + r;
+      for (int rr = 0; rr < kTailRows; ++rr) {
+        const int r = kFull ? lane + 32 * rr : (warp - 22) * 32 + lane + 64 * rr, kv = kv0 + r;
         const uint32_t krow = smem_u32(sK) + (uint32_t)r * 128u, vrow = smem_u32(sV) + (uint32_t)r * 128u;
         float sc = 0.f, dpv = 0.f;
 #pragma unroll 4
@@ -791,8 +907,8 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 8; ++i) v8[i] = 0.f;
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const int r = (warp - 22) * 32 + lane + 64 * rr;
+        for (int rr = 0; rr < kTailRows; ++rr) {
+          const int r = kFull ? lane + 32 * rr : (warp - 22) * 32 + lane + 64 * rr;
           const uint4 kk = ld_shared_u4(smem_u32(sK) + (uint32_t)r * 128u + (uint32_t)((cc ^ (r & 7)) * 16));
           const uint32_t kw[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
@@ -813,8 +929,8 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (lane < 8) atomicAdd(trow + (2 * cc + (lane >> 2)) * 512 + (lane & 3), val);
       }
     } else if (tail > 0) {  // timing experiment: no tail work
-      sm->tail_ds[(warp - 22) * 32 + lane] = sm->tail_ds[(warp - 22) * 32 + lane + 64] = 0.f;
-      sm->tail_pm[(warp - 22) * 32 + lane] = sm->tail_pm[(warp - 22) * 32 + lane + 64] = 0.f;
+      for (int r = kFull ? lane : (warp - 22) * 32 + lane; r < kTileB; r += kFull ? 32 : 64)
+        sm->tail_ds[r] = sm->tail_pm[r] = 0.f;
       mbar_arrive(&sm->tail_ready);
     }
   }
@@ -846,11 +962,19 @@ size_t tc_attn_bwd_workspace(int B, int N, int H, int hd) {
   return ws_dvec_bytes(B, N, H) + ws_dq_bytes(B, N, H) + ws_stat_bytes(B, N, H);
 }
 
-// Which instantiations use the transposed formulation: TVIT_ATTN_BWD_T bit 0 = without dropout, bit 1 = with dropout
-// (A-B timing; the default is what measured faster on B200).
-static int attn_bwd_t_mask() {
-  static const int m = [] { const char* e = getenv("TVIT_ATTN_BWD_T"); return e ? atoi(e) : TVIT_ATTN_BWD_T_DEFAULT; }();
+// Formulation of the kernel per instantiation (bit mask; DESIGN.md section 4.3 has the measurements):
+//   bit 0 / 1: transposed (S^T = K Q^T, P^T / dS^T as TMEM operands of dV / dK) without / with dropout
+//   bit 2 / 3: whole-tile S / dP MMAs + two issuing warps without / with dropout
+// 0 = key-half pipelined (default: fastest on B200 at the bench shapes).  TVIT_ATTN_BWD_T sets the initial value,
+// tvit_attn_bwd_variant() changes it at run time (tests run every variant against the oracle).
+static int& attn_bwd_t_mask() {
+  static int m = [] { const char* e = getenv("TVIT_ATTN_BWD_T"); return e ? atoi(e) : TVIT_ATTN_BWD_T_DEFAULT; }();
   return m;
+}
+int tc_attn_bwd_variant(int mask) {
+  const int old = attn_bwd_t_mask();
+  if (mask >= 0) attn_bwd_t_mask() = mask & 15;
+  return old;
 }
 
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* ws,
@@ -869,18 +993,14 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
 
   constexpr int smem_bytes = 2 * kTileBytesB + kQStages * 2 * kTileBytesB + 3 * kPBytes + 1024 + 1280;  // 226.25 KB
   int rc;
-  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false, false>, smem_bytes)) != TVIT_OK) return rc;
-  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true, false>, smem_bytes)) != TVIT_OK) return rc;
-  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false, true>, smem_bytes)) != TVIT_OK) return rc;
-  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true, true>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false, false, false>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true, false, false>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false, false, true>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true, false, true>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false, true, false>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true, true, false>, smem_bytes)) != TVIT_OK) return rc;
 
   TVIT_CUDA_OK(cudaMemsetAsync(dqacc, 0, dq_bytes, s));
-  {
-    const long long total = (long long)B * N * H;
-    attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-        (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, dvec, B, N, H);
-    TVIT_LAUNCH_OK();
-  }
   CUtensorMap tm_qkv, tm_do;
   if ((rc = make_tok_tmap(&tm_qkv, qkv, B, N, 3 * D)) != TVIT_OK) return rc;
   if ((rc = make_tok_tmap(&tm_do, dout, B, N, D)) != TVIT_OK) return rc;
@@ -893,20 +1013,25 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   const __nv_bfloat16* dop = (const __nv_bfloat16*)dout;
   const bool drop_on = dc.thr16 != 0;
   const bool transposed = (attn_bwd_t_mask() >> (drop_on ? 1 : 0)) & 1;
-  if (transposed) {
-    const long long total = (long long)B * H * nq * kTileB;
-    attn_bwd_stat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-        lse, dvec, stat, B * H, N, nq, drop_on ? log2f(dc.inv_keep) : 0.f, scale / dc.inv_keep);
+  const bool full = !transposed && ((attn_bwd_t_mask() >> (drop_on ? 3 : 2)) & 1);
+  {
+    const long long total = (long long)B * nq * kTileB * H;
+    attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse, dvec, stat, B, N, H, nq,
+        drop_on ? log2f(dc.inv_keep) : 0.f, scale / dc.inv_keep);
     TVIT_LAUNCH_OK();
   }
-#define TVIT_BWD_LAUNCH(DROP, T)                                                                                      \
-  tc_attn_bwd_kernel<DROP, T><<<grid, kAttnBwdThreads, smem_bytes, s>>>(tm_qkv, tm_do, qp, dop, lse, dvec, stat, dqacc, \
-                                                                        (__nv_bfloat16*)dqkv, dqkv_colsum, N, tail, H, \
-                                                                        scale, dc)
+#define TVIT_BWD_LAUNCH(DROP, T, F)                                                                               \
+  tc_attn_bwd_kernel<DROP, T, F><<<grid, kAttnBwdThreads, smem_bytes, s>>>(                                        \
+      tm_qkv, tm_do, qp, dop, lse, dvec, stat, dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, N, tail, H, scale, dc)
   if (drop_on) {
-    if (transposed) TVIT_BWD_LAUNCH(true, true); else TVIT_BWD_LAUNCH(true, false);
+    if (transposed) TVIT_BWD_LAUNCH(true, true, false);
+    else if (full) TVIT_BWD_LAUNCH(true, false, true);
+    else TVIT_BWD_LAUNCH(true, false, false);
   } else {
-    if (transposed) TVIT_BWD_LAUNCH(false, true); else TVIT_BWD_LAUNCH(false, false);
+    if (transposed) TVIT_BWD_LAUNCH(false, true, false);
+    else if (full) TVIT_BWD_LAUNCH(false, false, true);
+    else TVIT_BWD_LAUNCH(false, false, false);
   }
 #undef TVIT_BWD_LAUNCH
   TVIT_LAUNCH_OK();
@@ -920,3 +1045,9 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
 }
 
 }  // namespace tvit
+
+#ifdef TVIT_ATTN_TRACE
+extern "C" int tvit_attn_bwd_trace(long long* host_out, int n) {
+  return (int)cudaMemcpyFromSymbol(host_out, tvit::g_attn_trace, (size_t)n * sizeof(long long));
+}
+#endif

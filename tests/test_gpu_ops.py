@@ -317,6 +317,42 @@ def test_attention_dropout_mask_is_the_same_function_in_every_kernel(Bsz, N, H):
     assert rel_err(b[0], out0.float()) > 0.1
 
 
+@pytest.mark.parametrize("variant", [3, 12], ids=["transposed", "whole_tile_two_issuers"])
+@pytest.mark.parametrize("Bsz,N,H", [(1, 2049, 2), (2, 300, 3), (2, 129, 1)])
+def test_attention_backward_variants_agree(variant, Bsz, N, H):
+    """The tcgen05 backward kernel exists in three formulations (tvit_attn_bwd_variant, include/tvit.h): key-half
+    pipelined (default), transposed (P^T / dS^T as TMEM operands; its dropout masks go through an in-register 16 x 16
+    byte transpose) and whole-tile S / dP with two MMA-issuing warps.  All must produce the default's gradients -- with
+    dropout that means the identical mask -- and the SIMT engine's, for full and ragged tiles."""
+    hd = 64
+    D = H * hd
+    qkv = _rand((Bsz * N, 3 * D), L.BF16, 90, 0.7)
+    dout = _rand((Bsz * N, D), L.BF16, 91)
+    lib = L.load()
+    for drop in (None, (99, 5, 0.3)):
+        out = torch.empty((Bsz * N, D), dtype=torch.bfloat16, device=DEV)
+        lse = torch.empty((Bsz, H, N), device=DEV)
+        ops.attn_fwd(L.ENGINE_TCGEN05, L.BF16, qkv, out, lse, Bsz, N, H, hd, drop)
+        got = {}
+        prev = lib.tvit_attn_bwd_variant(-1)
+        try:
+            for v in (0, variant):
+                lib.tvit_attn_bwd_variant(v)
+                dqkv = torch.full_like(qkv, float("nan"))
+                cs = torch.zeros(3 * D, device=DEV)
+                ops.attn_bwd(L.ENGINE_TCGEN05, L.BF16, qkv, out, dout, lse, dqkv, Bsz, N, H, hd, drop, colsum=cs)
+                got[v] = (dqkv.float(), cs.clone())
+        finally:
+            lib.tvit_attn_bwd_variant(prev)
+        ref = torch.empty_like(qkv)
+        ops.attn_bwd(L.ENGINE_SIMT, L.BF16, qkv, out, dout, lse, ref, Bsz, N, H, hd, drop)
+        assert torch.isfinite(got[variant][0]).all()
+        # same operands, same masks, same bf16 roundings of P and dS: the variants differ only in summation order
+        assert rel_err(got[variant][0], got[0][0]) < 2e-3, drop
+        assert rel_err(got[variant][0], ref.float()) < 2e-2, drop
+        assert rel_err(got[variant][1], got[0][1]) < 2e-3, drop
+
+
 @pytest.mark.parametrize("engine,dtype,tag", ATTN_ENGINES, ids=[e[2] for e in ATTN_ENGINES])
 def test_attention_dropout_consistency(engine, dtype, tag):
     """With dropout the mask cannot match torch's Philox stream; check keep-rate, 1/(1-p) scaling and
