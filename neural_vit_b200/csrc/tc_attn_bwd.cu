@@ -216,22 +216,25 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const 
 }
 
 // dq accumulator layout: [(b*H+h)][q tile][16 chunks][128 rows][4 fp32]
-// thread = (row r, group of 4 chunks): four coalesced float4 reads, one full-sector 32-byte bf16 store
-__global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_bfloat16* __restrict__ dqkv,
-                                          float* __restrict__ colsum, int B, int N, int H, int nq) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long total = (long long)B * H * nq * 4 * 128;  // a multiple of the block size: whole blocks drop out
-  if (idx >= total) return;
-  const int r = (int)(idx & 127);
-  const int cg = (int)((idx >> 7) & 3);
-  const long long t = idx >> 9;  // (b*H+h)*nq + i
-  const int i = (int)(t % nq);
-  const long long bh = t / nq;
+// thread = (row r, group of 4 chunks): four coalesced float4 reads, one full-sector 32-byte bf16 store.  A 512-thread
+// block walks the query tiles i = blockIdx.y, blockIdx.y + gridDim.y, ... of one (b, h), so that the dq part of the
+// qkv-bias gradient (column sums) is accumulated in registers over the tiles and leaves the block as 64 atomics
+// (one warp-level butterfly and one atomic per 32 rows and tile put 6.7 M same-address atomics on 384 words at C2).
+__global__ void __launch_bounds__(512)
+attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum,
+                          int N, int H, int nq) {
+  __shared__ float red[4][64];
+  const int r = threadIdx.x & 127, cg = threadIdx.x >> 7;
+  const long long bh = blockIdx.x;
   const int h = (int)(bh % H), b = (int)(bh / H);
-  const int q = i * kTileB + r;
-  const float* src = dqacc + ((t * 16 + 4 * cg) * 128 + r) * 4;
-  float f[16];
-  if (q < N) {
+  float cs[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) cs[k] = 0.f;
+  for (int i = blockIdx.y; i < nq; i += gridDim.y) {
+    const int q = i * kTileB + r;
+    if (q >= N) continue;
+    const float* src = dqacc + (((bh * nq + i) * 16 + 4 * cg) * 128 + r) * 4;
+    float f[16];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float4 x = *reinterpret_cast<const float4*>(src + (long long)k * 512);
@@ -242,14 +245,17 @@ __global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_
     for (int k = 0; k < 8; ++k) v[k] = pack_bf16(f[2 * k], f[2 * k + 1]);
     st_global_b32x8(dqkv + ((long long)b * N + q) * (3LL * H * kHdB) + h * kHdB + 16 * cg, v[0], v[1], v[2], v[3], v[4],
                     v[5], v[6], v[7]);
-  } else {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) f[k] = 0.f;
+    for (int k = 0; k < 16; ++k) cs[k] += f[k];
   }
-  if (colsum) {  // dq part of the qkv-bias gradient: a warp holds 32 rows of the same 16 columns
-    const int lane = threadIdx.x & 31;
-    const float tot = warp_colsum16(f, lane);
-    if ((lane & 1) == 0) atomicAdd(colsum + h * kHdB + 16 * cg + (lane >> 1), tot);
+  if (colsum) {  // a warp holds 32 rows of the same 16 columns; the four warps of a column group meet in smem
+    const int lane = threadIdx.x & 31, wq = (threadIdx.x >> 5) & 3;
+    const float tot = warp_colsum16(cs, lane);
+    if ((lane & 1) == 0) red[wq][16 * cg + (lane >> 1)] = tot;
+    __syncthreads();
+    if (threadIdx.x < 64)
+      atomicAdd(colsum + h * kHdB + threadIdx.x,
+                (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]));
   }
 }
 
@@ -1036,9 +1042,9 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
 #undef TVIT_BWD_LAUNCH
   TVIT_LAUNCH_OK();
   {
-    const long long total = (long long)B * H * nq * 4 * 128;
-    attn_bwd_dq_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, B,
-                                                                              N, H, nq);
+    const int split = nq >= 4 ? 4 : 1;  // B H x 4 blocks of 512 threads: several waves even at small B H
+    attn_bwd_dq_finish_kernel<<<dim3((unsigned)(B * H), split), 512, 0, s>>>(dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, N, H,
+                                                                           nq);
     TVIT_LAUNCH_OK();
   }
   return TVIT_OK;

@@ -123,6 +123,10 @@ def main():
             csq = torch.zeros(3 * D, device=DEV)
             ms = timeit(lambda: ops.attn_bwd(E, T, qkv, out, dout, lse, dqkv, B, N, H, hd, d, colsum=csq), a.reps)
             report(f"attn bwd {tag} + fused qkv-bias colsum", ms, 2 * fl)
+            # again in the opposite order: under the power cap the clocks sag over a long run of launches, which would
+            # otherwise always be charged to whichever variant is timed last
+            ms = timeit(lambda: ops.attn_bwd(E, T, qkv, out, dout, lse, dqkv, B, N, H, hd, d), a.reps)
+            report(f"attn bwd {tag} (again, after the colsum variant)", ms, 2 * fl)
         del qkv, out, dout, dqkv
 
     if "elem" in only:
