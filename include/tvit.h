@@ -126,15 +126,21 @@ int tvit_gemm(const tvit_gemm_args* args, tvit_stream_t stream);
  * Dropout on the probabilities: element index = ((b*H + h)*N + q)*Np + k, Np = N rounded up to 16.
  * Replaces model.py:108-115 (reshape/permute, q@k^T*scale, softmax, attn_drop, @v, transpose).
  * ------------------------------------------------------------------------------------------- */
+/* keepbits (optional, tcgen05 engine with dropout only; NULL = off): a cache of the dropout site's keep flags, one
+ * 32-bit word per 16-key group -- tvit_attn_keepbits_bytes() bytes, layout [(b,h)][q tile][key tile][128 rows][8 groups],
+ * bit t / 16+t of a word = keep flag of key 2t / 2t+1 of the group.  tvit_attn_fwd writes it, tvit_attn_bwd of the same
+ * (qkv, drop) reads it instead of running the generator again: same masks, ~8 % fewer instructions in the backward
+ * kernel.  The cache is a pure function of (drop, shape); passing NULL to either call changes no result. */
+size_t tvit_attn_keepbits_bytes(int engine, int B, int N, int H); /* 0 for engines that do not use the cache */
 int tvit_attn_fwd(int engine, int dtype, const void* qkv, void* out, float* lse, int B, int N, int H, int hd,
-                  const tvit_dropout* drop, tvit_stream_t stream);
+                  const tvit_dropout* drop, void* keepbits, tvit_stream_t stream);
 size_t tvit_attn_bwd_workspace_bytes(int engine, int dtype, int B, int N, int H, int hd);
 /* dqkv : [B*N, 3*H*hd] act.  workspace must hold tvit_attn_bwd_workspace_bytes() bytes.
  * dqkv_colsum (optional, fp32 [3*H*hd], caller zero-fills): += column sums of dqkv taken in fp32 before rounding --
  * the gradient of the qkv bias (model.py:101), folded into the kernels that produce dqkv. */
 int tvit_attn_bwd(int engine, int dtype, const void* qkv, const void* out, const void* dout, const float* lse,
                   void* dqkv, void* workspace, size_t workspace_bytes, int B, int N, int H, int hd,
-                  const tvit_dropout* drop, float* dqkv_colsum, tvit_stream_t stream);
+                  const tvit_dropout* drop, float* dqkv_colsum, const void* keepbits, tvit_stream_t stream);
 /* Formulation of the tcgen05 attention backward kernel (bit 0 / 1: transposed form without / with dropout; bit 2 / 3:
  * whole-tile S / dP MMAs with two issuing warps without / with dropout; 0 = key-half pipelined, the default).  All
  * variants compute the same function with the same dropout masks; the switch exists for A-B timing and for the parity

@@ -52,11 +52,12 @@ SIGNATURES = {
     "tvit_version": (c_int, []),
     "tvit_device_check": (c_int, [c_int]),
     "tvit_gemm": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "tvit_attn_keepbits_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "tvit_attn_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                              ctypes.POINTER(Dropout), c_void_p]),
+                              ctypes.POINTER(Dropout), c_void_p, c_void_p]),
     "tvit_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "tvit_attn_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                              c_int, c_int, c_int, c_int, ctypes.POINTER(Dropout), c_void_p, c_void_p]),
+                              c_int, c_int, c_int, c_int, ctypes.POINTER(Dropout), c_void_p, c_void_p, c_void_p]),
     "tvit_attn_bwd_variant": (c_int, [c_int]),
     "tvit_attn_probs": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tvit_im2col": (c_int, [c_void_p, c_void_p, c_int] + [c_int] * 7 + [c_void_p]),

@@ -41,12 +41,13 @@ int simt_attn_bwd(int dtype, const void* qkv, const void* out, const void* dout,
                   void* ws, size_t ws_bytes, int B, int N, int H, int hd, const tvit_dropout* drop, cudaStream_t s);
 int attn_probs(int dtype, const void* qkv, float* probs, int B, int N, int H, int hd, cudaStream_t s);
 int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, const tvit_dropout* drop,
-                cudaStream_t s);
+                void* keepbits, cudaStream_t s);
+size_t tc_attn_keepbits_bytes(int B, int N, int H);
 size_t tc_attn_bwd_workspace(int B, int N, int H, int hd);
 int tc_attn_bwd_variant(int mask);
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* ws,
                 size_t ws_bytes, int B, int N, int H, int hd, const tvit_dropout* drop, float* dqkv_colsum,
-                cudaStream_t s);
+                const void* keepbits, cudaStream_t s);
 
 }  // namespace tvit
 
@@ -99,16 +100,20 @@ extern "C" int tvit_gemm(const tvit_gemm_args* a, tvit_stream_t stream) {
 }
 
 extern "C" int tvit_attn_fwd(int engine, int dtype, const void* qkv, void* out, float* lse, int B, int N, int H,
-                             int hd, const tvit_dropout* drop, tvit_stream_t stream) {
+                             int hd, const tvit_dropout* drop, void* keepbits, tvit_stream_t stream) {
   TVIT_CHECK_ARG(qkv && out && lse, "attn_fwd: null pointer");
   TVIT_CHECK_ARG(B > 0 && N > 0 && H > 0 && hd > 0, "attn_fwd: bad shape");
   cudaStream_t s = (cudaStream_t)stream;
   if (engine == TVIT_ENGINE_SIMT) return simt_attn_fwd(dtype, qkv, out, lse, B, N, H, hd, drop, s);
   if (engine == TVIT_ENGINE_TCGEN05) {
     TVIT_CHECK_ARG(dtype == TVIT_BF16, "attn_fwd: tcgen05 engine needs bf16");
-    return tc_attn_fwd(qkv, out, lse, B, N, H, hd, drop, s);
+    return tc_attn_fwd(qkv, out, lse, B, N, H, hd, drop, keepbits, s);
   }
   return fail(TVIT_ERR_BAD_ARG, "attn_fwd: unknown engine %d", engine);
+}
+
+extern "C" size_t tvit_attn_keepbits_bytes(int engine, int B, int N, int H) {
+  return engine == TVIT_ENGINE_TCGEN05 ? tc_attn_keepbits_bytes(B, N, H) : 0;
 }
 
 extern "C" size_t tvit_attn_bwd_workspace_bytes(int engine, int dtype, int B, int N, int H, int hd) {
@@ -119,7 +124,8 @@ extern "C" size_t tvit_attn_bwd_workspace_bytes(int engine, int dtype, int B, in
 
 extern "C" int tvit_attn_bwd(int engine, int dtype, const void* qkv, const void* out, const void* dout,
                              const float* lse, void* dqkv, void* workspace, size_t workspace_bytes, int B, int N, int H,
-                             int hd, const tvit_dropout* drop, float* dqkv_colsum, tvit_stream_t stream) {
+                             int hd, const tvit_dropout* drop, float* dqkv_colsum, const void* keepbits,
+                             tvit_stream_t stream) {
   TVIT_CHECK_ARG(qkv && out && dout && lse && dqkv, "attn_bwd: null pointer");
   TVIT_CHECK_ARG(B > 0 && N > 0 && H > 0 && hd > 0, "attn_bwd: bad shape");
   cudaStream_t s = (cudaStream_t)stream;
@@ -130,7 +136,8 @@ extern "C" int tvit_attn_bwd(int engine, int dtype, const void* qkv, const void*
   }
   if (engine == TVIT_ENGINE_TCGEN05) {
     TVIT_CHECK_ARG(dtype == TVIT_BF16, "attn_bwd: tcgen05 engine needs bf16");
-    return tc_attn_bwd(qkv, out, dout, lse, dqkv, workspace, workspace_bytes, B, N, H, hd, drop, dqkv_colsum, s);
+    return tc_attn_bwd(qkv, out, dout, lse, dqkv, workspace, workspace_bytes, B, N, H, hd, drop, dqkv_colsum, keepbits,
+                       s);
   }
   return fail(TVIT_ERR_BAD_ARG, "attn_bwd: unknown engine %d", engine);
 }

@@ -309,6 +309,10 @@ __device__ __forceinline__ uint32_t drop_thr8(const DropCfg& c, unsigned long lo
 }
 // random bytes for the 16 consecutive elements [16 g, 16 g + 16): element j is byte (j & 3) of word j >> 2
 __device__ __forceinline__ void drop_bits16(const DropCfg& c, unsigned long long group16, uint32_t out[4]) {
+#ifdef TVIT_EXPERIMENT_NOPHILOX  // timing experiment only (wrong masks): what the generator itself costs a kernel
+  out[0] = (uint32_t)group16 * 0x9E3779B1u; out[1] = out[0] ^ c.rk0[1]; out[2] = out[0] + c.rk1[2]; out[3] = ~out[0];
+  return;
+#endif
   uint4 r = philox4x32_7(c, group16);
   out[0] = r.x;
   out[1] = r.y;

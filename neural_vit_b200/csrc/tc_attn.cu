@@ -53,7 +53,7 @@ template <bool kDrop>
 __global__ void __launch_bounds__(kAttnFwdThreads, 2)
 tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv,
                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int tail, int H, float scale_log2,
-                   DropCfg drop) {
+                   DropCfg drop, uint32_t* __restrict__ keepbits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -191,6 +191,9 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
       m2 = tail_score() * scale_log2;
       if (hf == 0) l = 1.0f;  // ex2(0); the partners' row sums are added at the end: only one of them counts the tail
     }
+    // keep-bit records of this CTA's query tile: [(b,h)][q tile][key tile][row][8 groups] 32-bit words
+    const int nkt_all = (N + kTile - 1) / kTile;
+    uint32_t* kb_tile = keepbits + ((((long long)b * H + h) * gridDim.x + blockIdx.x) * nkt_all * kTile + r) * 8 + hf * 4;
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&sm->s_full, (uint32_t)j & 1u);
       tc_fence_after();
@@ -240,6 +243,7 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
       // ---- pass B: exponentials, partial row sum (of the un-dropped probabilities), dropout mask, bf16 pack ----
       // (the 1/(1-p) factor of kept elements is applied once to O in the epilogue)
       f32x2 rs01 = pk2(0.f, 0.f), rs23 = rs01;
+      uint32_t kbw[4] = {0, 0, 0, 0};  // keep bits of this thread's four 16-key groups of the tile
       const f32x2 sl2 = pk2(scale_log2, scale_log2), nm2 = pk2(-m_new, -m_new);
       const unsigned long long g0 = (rowe + (unsigned long long)j * kTile + hf * 64) >> 4;  // 16-element groups
 #pragma unroll
@@ -260,7 +264,7 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
         uint32_t pk[16];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {  // one Philox call per 16 keys (common.cuh: attention-probability dropout)
-          uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0;
+          uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0, kb = 0;
           if (kDrop) {
             drop_bits16(drop, g0 + c2 * 2 + g, w);
             tg2 = drop_tgc(drop_thr8(drop, g0 + c2 * 2 + g));
@@ -277,12 +281,16 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
             rs23 = add2(rs23, p23);
             uint32_t v01 = pack_bf16_2(p01), v23 = pack_bf16_2(p23);
             if (kDrop) {
-              v01 &= drop_keep_mask2<0>(w[u], tg2);
-              v23 &= drop_keep_mask2<1>(w[u], tg2);
+              const uint32_t m01 = drop_keep_mask2<0>(w[u], tg2), m23 = drop_keep_mask2<1>(w[u], tg2);
+              v01 &= m01;
+              v23 &= m23;
+              // keep-bit record of the group (include/tvit.h: tvit_attn_keepbits_bytes): one LOP3 per element pair
+              kb |= (m01 & (0x00010001u << (2 * u))) | (m23 & (0x00010001u << (2 * u + 1)));
             }
             pk[g * 8 + u * 2] = v01;
             pk[g * 8 + u * 2 + 1] = v23;
           }
+          if (kDrop) kbw[c2 * 2 + g] = kb;
         }
         tmem_st16(tP + lane_off + hf * 32 + c2 * 16, pk);
       }
@@ -291,6 +299,8 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
       up2(rs23, rs2, rs3);
       l = l * corr + ((rs0 + rs1) + (rs2 + rs3));
       m2 = m_new;
+      if (kDrop && keepbits)  // record (q tile, key tile j): [row r][8 groups] words; this thread owns groups hf*4 .. +3
+        st_global_v4(kb_tile + (long long)j * (kTile * 8), kbw[0], kbw[1], kbw[2], kbw[3]);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -303,7 +313,12 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
     float pt = 0.f;  // tail key's probability, computed while the last P V MMA is still in flight
     if (tail > 0) {
       pt = ex2_approx(fmaf(tail_score(), scale_log2, -m2));
-      if (kDrop && !drop_keep(drop, rowe + (unsigned long long)Nk)) pt = 0.f;
+      if (kDrop) {
+        const bool keep_t = drop_keep(drop, rowe + (unsigned long long)Nk);
+        if (!keep_t) pt = 0.f;
+        // the tail key is element 0 of group 0 of key tile nkv (the backward CTA of that key tile reads it there)
+        if (keepbits && hf == 0) kb_tile[(long long)nkv * (kTile * 8)] = keep_t ? 1u : 0u;
+      }
     }
     mbar_wait(&sm->pv_done, (uint32_t)(nkv - 1) & 1u);
     tc_fence_after();
@@ -356,8 +371,14 @@ static int make_qkv_tmap(CUtensorMap* tm, const void* qkv, int B, int N, int D3,
   return make_tmap_bf16(tm, qkv, 3, dims, strides, box);
 }
 
+// keep-bit cache of the attention-probability dropout site (include/tvit.h): one 32-bit word per 16-key group
+size_t tc_attn_keepbits_bytes(int B, int N, int H) {
+  const size_t nt = (size_t)((N + kTile - 1) / kTile);
+  return (size_t)B * H * nt * nt * kTile * 8 * sizeof(uint32_t);
+}
+
 int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, const tvit_dropout* drop,
-                cudaStream_t s) {
+                void* keepbits, cudaStream_t s) {
   if (hd != kHd) return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 attention supports head_dim 64 only (got %d)", hd);
   const int D = H * hd;
   if (D % 8 != 0) return fail(TVIT_ERR_BAD_ARG, "attention: embed dim must be a multiple of 8");
@@ -373,9 +394,11 @@ int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int
   const int tail = attn_tail(N, 1);
   const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv;
   if (dc.thr16 != 0)
-    tc_attn_fwd_kernel<true><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, qp, (__nv_bfloat16*)out, lse, N, tail, H, scale_log2, dc);
+    tc_attn_fwd_kernel<true><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, qp, (__nv_bfloat16*)out, lse, N, tail, H, scale_log2, dc,
+                                                                       (uint32_t*)keepbits);
   else
-    tc_attn_fwd_kernel<false><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, qp, (__nv_bfloat16*)out, lse, N, tail, H, scale_log2, dc);
+    tc_attn_fwd_kernel<false><<<grid, kAttnFwdThreads, smem_bytes, s>>>(tm, qp, (__nv_bfloat16*)out, lse, N, tail, H, scale_log2, dc,
+                                                                        nullptr);
   TVIT_LAUNCH_OK();
   return TVIT_OK;
 }

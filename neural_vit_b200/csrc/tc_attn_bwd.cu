@@ -266,13 +266,17 @@ attn_bwd_dq_finish_kernel(const float* __restrict__ dqacc, __nv_bfloat16* __rest
 // kFull (non-transposed only): S and dP are issued as whole N = 128 MMAs (4 x 107 clk instead of 8 x 75 clk,
 // profiles/r2_mma_rate.txt) into the single-buffered S / dP columns as soon as every softmax warp has loaded tile i's
 // scores -- i.e. half-way through the softmax of tile i -- instead of half by half, and dQ always takes dS from TMEM.
-template <bool kDrop, bool kT, bool kFull>
+// kBits (default formulation with dropout only): the keep flags come from the cache the forward kernel wrote
+// (include/tvit.h: tvit_attn_keepbits_bytes) instead of from the generator -- two 32-bit loads and a shift + prmt per
+// element pair replace two Philox calls and the byte compares per tile and thread.
+template <bool kDrop, bool kT, bool kFull, bool kBits = false>
 __global__ void __launch_bounds__(kAttnBwdThreads, 1)
 tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ dvec, const float* __restrict__ stat,
                    float* __restrict__ dqacc, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int N,
-                   int tail_arg, int H, float scale, DropCfg drop) {
+                   int tail_arg, int H, float scale, DropCfg drop, const uint32_t* __restrict__ keepbits) {
+  static_assert(!kBits || (kDrop && !kT && !kFull), "the keep-bit cache feeds the default dropout instantiation only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;
@@ -712,14 +716,27 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     // 32-bit row term (q * npad / 16 < 2^32 for every N this kernel accepts)
     const uint32_t npad16 = (uint32_t)((N + 15) >> 4);
     const unsigned long long grp_cta = (attn_drop_row_base(b, H, h, N, 0) + (unsigned long long)kv0) >> 4;
+    // keep-bit records of this key tile: [(b,h)][q tile][key tile][row][8 groups]; this thread reads groups chunk, 4 + chunk
+    const uint32_t* kb_row = kBits ? keepbits + ((((long long)b * H + h) * nqt * nqt + jt) * kTileB + r) * 8 + chunk : nullptr;
+    const int kb_qstride = nqt * kTileB * 8;
+    uint32_t kb_next0 = 0, kb_next1 = 0;
+    if (kBits) {
+      kb_next0 = __ldg(kb_row + qt * kb_qstride);
+      kb_next1 = __ldg(kb_row + qt * kb_qstride + 4);
+    }
     for (int i = 0; i < nq; ++i) {
       const float nlse2 = nl_next, negDq = nd_next;
       const f32x2 nlse2_2 = pk2(nlse2, nlse2), negDq_2 = pk2(negDq, negDq);
       const unsigned long long grp_row = grp_cta + (unsigned long long)((uint32_t)(qt * kTileB + r) * npad16);
+      const uint32_t kb0 = kb_next0, kb1 = kb_next1;
       {  // prefetch the next tile's row statistics so the global-load latency is off the critical path
         qt = (qt + 1 == nq) ? 0 : qt + 1;
         nl_next = stat_row[qt * 256];
         nd_next = stat_row[qt * 256 + 128];
+        if (kBits) {
+          kb_next0 = __ldg(kb_row + qt * kb_qstride);
+          kb_next1 = __ldg(kb_row + qt * kb_qstride + 4);
+        }
       }
       const uint32_t aDSbuf = smem_u32(sDS) + (uint32_t)(i & 1) * kPBytes;
 #pragma unroll
@@ -737,7 +754,8 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (lane == 0) mbar_arrive(&sm->s_free[hf]);  // this half's S / dP columns may be refilled
         uint32_t pk[8], dk[8];
         uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0;
-        if (kDrop) {  // this thread's 16 keys are exactly one Philox group (common.cuh)
+        const uint32_t kbw = hf == 0 ? kb0 : kb1;  // kBits: bit t / 16 + t = keep flag of element 2t / 2t + 1
+        if (kDrop && !kBits) {  // this thread's 16 keys are exactly one Philox group (common.cuh)
           const unsigned long long grp = grp_row + (unsigned long long)(hf * 4 + chunk);
           drop_bits16(drop, grp, w);
           tg2 = drop_tgc(drop_thr8(drop, grp));
@@ -751,7 +769,9 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           const f32x2 p = pk2(ex2_approx(e0), ex2_approx(e1));
           const f32x2 a = fma2(pk2(__uint_as_float(dp[2 * t]), __uint_as_float(dp[2 * t + 1])), scale_2, negDq_2);
           if (kDrop) {
-            const uint32_t m = (t & 1) ? drop_keep_mask2<1>(w[t >> 1], tg2) : drop_keep_mask2<0>(w[t >> 1], tg2);
+            const uint32_t m = kBits   ? prmt<0xBB99u>(kbw << (15 - t), 0u)
+                               : (t & 1) ? drop_keep_mask2<1>(w[t >> 1], tg2)
+                                         : drop_keep_mask2<0>(w[t >> 1], tg2);
             const uint32_t kept = pack_bf16_2(mul2(p, a)), dropped = pack_bf16_2(mul2(p, negDq_2));
             pk[t] = pack_bf16_2(p) & m;
             dk[t] = (kept & m) | (dropped & ~m);
@@ -985,7 +1005,7 @@ int tc_attn_bwd_variant(int mask) {
 
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* ws,
                 size_t ws_bytes, int B, int N, int H, int hd, const tvit_dropout* drop, float* dqkv_colsum,
-                cudaStream_t s) {
+                const void* keepbits, cudaStream_t s) {
   if (hd != kHdB) return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 attention supports head_dim 64 only (got %d)", hd);
   if (!ws || ws_bytes < tc_attn_bwd_workspace(B, N, H, hd))
     return fail(TVIT_ERR_BAD_ARG, "attn_bwd: workspace too small (%zu < %zu)", ws_bytes,
@@ -1005,6 +1025,7 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true, false, true>, smem_bytes)) != TVIT_OK) return rc;
   if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<false, true, false>, smem_bytes)) != TVIT_OK) return rc;
   if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true, true, false>, smem_bytes)) != TVIT_OK) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)tc_attn_bwd_kernel<true, false, false, true>, smem_bytes)) != TVIT_OK) return rc;
 
   TVIT_CUDA_OK(cudaMemsetAsync(dqacc, 0, dq_bytes, s));
   CUtensorMap tm_qkv, tm_do;
@@ -1029,10 +1050,15 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   }
 #define TVIT_BWD_LAUNCH(DROP, T, F)                                                                               \
   tc_attn_bwd_kernel<DROP, T, F><<<grid, kAttnBwdThreads, smem_bytes, s>>>(                                        \
-      tm_qkv, tm_do, qp, dop, lse, dvec, stat, dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, N, tail, H, scale, dc)
+      tm_qkv, tm_do, qp, dop, lse, dvec, stat, dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, N, tail, H, scale, dc,   \
+      (const uint32_t*)keepbits)
   if (drop_on) {
     if (transposed) TVIT_BWD_LAUNCH(true, true, false);
     else if (full) TVIT_BWD_LAUNCH(true, false, true);
+    else if (keepbits)
+      tc_attn_bwd_kernel<true, false, false, true><<<grid, kAttnBwdThreads, smem_bytes, s>>>(
+          tm_qkv, tm_do, qp, dop, lse, dvec, stat, dqacc, (__nv_bfloat16*)dqkv, dqkv_colsum, N, tail, H, scale, dc,
+          (const uint32_t*)keepbits);
     else TVIT_BWD_LAUNCH(true, false, false);
   } else {
     if (transposed) TVIT_BWD_LAUNCH(false, true, false);

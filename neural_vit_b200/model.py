@@ -243,6 +243,10 @@ class _EmbedFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 # encoder block (model.py:151-178): x + dp(ls1(attn(ln1 x)));  x + dp(ls2(mlp(ln2 x)))
 # ---------------------------------------------------------------------------------------------
+# TVIT_ATTN_KEEPBITS=0 makes the backward kernel regenerate the attention dropout masks (A-B timing; same results)
+_USE_KEEPBITS = os.environ.get("TVIT_ATTN_KEEPBITS", "1") != "0"
+
+
 def _block_forward(h, n1w, n1b, qkvw, qkvb, pw, pb, g1, n2w, n2b, f1w, f1b, f2w, f2b, g2, s1, s2,
                    rt: _Ctx, sh: _Shadows, layer: int, need_grad: bool):
     """All launches of one encoder block's forward.  Returns (h_out, saved intermediates, dropout specs)."""
@@ -271,7 +275,10 @@ def _block_forward(h, n1w, n1b, qkvw, qkvb, pw, pb, g1, n2w, n2b, f1w, f1b, f2w,
     ops.gemm(E, T, y1, qkv_w, M, 3 * D, D, epilogue=L.EPI_STORE, out=qkv, bias=qkvb)
     ao = _empty((M, D), td, dev)
     lse = _empty((B, H, N), torch.float32, dev)
-    ops.attn_fwd(rt.attn_engine, T, qkv, ao, lse, B, N, H, hd, d_attn)
+    # dropout keep-flag cache: written by the forward kernel, read by the backward kernel instead of regenerating the
+    # masks (include/tvit.h); only allocated when a backward will follow
+    keepbits = ops.attn_keepbits(rt.attn_engine, B, N, H, d_attn, dev) if need_grad and _USE_KEEPBITS else None
+    ops.attn_fwd(rt.attn_engine, T, qkv, ao, lse, B, N, H, hd, d_attn, keepbits=keepbits)
     h_mid = torch.empty_like(h)
     ops.gemm(E, T, ao, proj_w, M, D, D, epilogue=L.EPI_RESIDUAL, out=h_mid, bias=pb, resid=h, gamma=g1,
              row_scale=s1, rows_per_group=N, drop=d_proj)
@@ -286,7 +293,7 @@ def _block_forward(h, n1w, n1b, qkvw, qkvb, pw, pb, g1, n2w, n2b, f1w, f1b, f2w,
     ops.gemm(E, T, act, fc2_w, M, D, hid, epilogue=L.EPI_RESIDUAL, out=h_out, bias=f2b, resid=h_mid, gamma=g2,
              row_scale=s2, rows_per_group=N, drop=d_fc2)
     saved = (h, y1, mean1, rstd1, qkv, ao, lse, h_mid, y2, mean2, rstd2, hpre, act,
-             n1w, qkvw, pw, pb, g1, n2w, f1w, f2w, f2b, g2, s1, s2, qkv_wt, proj_wt, fc1_wt, fc2_wt)
+             n1w, qkvw, pw, pb, g1, n2w, f1w, f2w, f2b, g2, s1, s2, qkv_wt, proj_wt, fc1_wt, fc2_wt, keepbits)
     return h_out, saved, (d_attn, d_proj, d_fc1, d_fc2)
 
 
@@ -309,7 +316,7 @@ class _BlockFn(torch.autograd.Function):
     def backward(ctx, g_out):
         (h, y1, mean1, rstd1, qkv, ao, lse, h_mid, y2, mean2, rstd2, hpre, act,
          n1w, qkvw, pw, pb, g1, n2w, f1w, f2w, f2b, g2, s1, s2,
-         qkv_wt, proj_wt, fc1_wt, fc2_wt) = ctx.saved_tensors
+         qkv_wt, proj_wt, fc1_wt, fc2_wt, keepbits) = ctx.saved_tensors
         rt, cfg = ctx.rt, ctx.rt.cfg
         sk = ctx.sinks[0] if ctx.sinks is not None else None
         d_attn, d_proj, d_fc1, d_fc2 = ctx.drops
@@ -389,7 +396,8 @@ class _BlockFn(torch.autograd.Function):
         # colsum(dqkv) (the qkv-bias gradient) is folded into the attention-backward kernels when that is a net win:
         # with dropout the issue-bound kernel hides it (+0.13 ms vs 0.22 ms for a separate pass), without it does not
         fuse_cs = d_attn is not None or rt.attn_engine != L.ENGINE_TCGEN05
-        ops.attn_bwd(rt.attn_engine, T, qkv, ao, dao, lse, dqkv, B, N, H, hd, d_attn, colsum=d_qkvb if fuse_cs else None)
+        ops.attn_bwd(rt.attn_engine, T, qkv, ao, dao, lse, dqkv, B, N, H, hd, d_attn, colsum=d_qkvb if fuse_cs else None,
+                     keepbits=keepbits)
         if not fuse_cs:
             ops.colsum(dqkv, T, M, 3 * D, 3 * D, d_qkvb)
         d_qkvw, _ = _dst(sk, I_QKVW, (3 * D, D), dev)

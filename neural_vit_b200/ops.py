@@ -125,11 +125,20 @@ def gemm(engine: int, dtype: int, a: torch.Tensor, b: torch.Tensor, M: int, N: i
         L.check(L.load().tvit_gemm(ctypes.byref(args), _stream()), "tvit_gemm")
 
 
-def attn_fwd(engine, dtype, qkv, out, lse, B, N, H, hd, drop: DropSpec = None) -> None:
+def attn_keepbits(engine, B, N, H, drop: DropSpec, device) -> Optional[torch.Tensor]:
+    """Buffer for the dropout keep-flag cache that attn_fwd fills and attn_bwd reads (include/tvit.h), or None when
+    the engine / call does not use one."""
+    if drop is None or drop[2] <= 0.0:
+        return None
+    nbytes = int(L.load().tvit_attn_keepbits_bytes(engine, B, N, H))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes else None
+
+
+def attn_fwd(engine, dtype, qkv, out, lse, B, N, H, hd, drop: DropSpec = None, keepbits=None) -> None:
     _count("attn_fwd")
     with _timed("attn_fwd"):
         L.check(L.load().tvit_attn_fwd(engine, dtype, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, hd,
-                                       _drop_ptr(drop), _stream()), "tvit_attn_fwd")
+                                       _drop_ptr(drop), _ptr(keepbits), _stream()), "tvit_attn_fwd")
 
 
 # grow-only scratch buffers, one per (device, stream): every use is stream-ordered on the stream it is keyed by, so
@@ -146,7 +155,8 @@ def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     return ws
 
 
-def attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, B, N, H, hd, drop: DropSpec = None, colsum=None) -> None:
+def attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, B, N, H, hd, drop: DropSpec = None, colsum=None,
+             keepbits=None) -> None:
     lib = L.load()
     nbytes = int(lib.tvit_attn_bwd_workspace_bytes(engine, dtype, B, N, H, hd))
     ws = workspace(nbytes, qkv.device)
@@ -154,7 +164,7 @@ def attn_bwd(engine, dtype, qkv, out, dout, lse, dqkv, B, N, H, hd, drop: DropSp
     with _timed("attn_bwd"):
         L.check(lib.tvit_attn_bwd(engine, dtype, qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
                                   dqkv.data_ptr(), ws.data_ptr(), nbytes, B, N, H, hd, _drop_ptr(drop), _ptr(colsum),
-                                  _stream()),
+                                  _ptr(keepbits), _stream()),
                 "tvit_attn_bwd")
 
 

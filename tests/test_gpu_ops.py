@@ -353,6 +353,55 @@ def test_attention_backward_variants_agree(variant, Bsz, N, H):
         assert rel_err(got[variant][1], got[0][1]) < 2e-3, drop
 
 
+@pytest.mark.parametrize("Bsz,N,H,p", [(1, 2049, 2, 0.1), (2, 300, 3, 0.3), (2, 129, 1, 0.1), (1, 257, 2, 0.75),
+                                       (2, 128, 1, 0.5), (1, 77, 2, 0.1)])
+def test_attention_keepbits_cache_reproduces_the_generated_masks(Bsz, N, H, p):
+    """tvit_attn_fwd can record the dropout keep flags it applied (include/tvit.h: tvit_attn_keepbits_bytes) and
+    tvit_attn_bwd can read them instead of running the generator again.  The cache is the same function of
+    (seed, site, element), so the backward result must be BIT-identical with and without it -- for full, ragged and
+    128 m + 1 token counts (where the tail key's flag takes the scalar path), for p above 1/2, and with the forward
+    output unchanged by the recording."""
+    hd = 64
+    D = H * hd
+    qkv = _rand((Bsz * N, 3 * D), L.BF16, 92, 0.7)
+    dout = _rand((Bsz * N, D), L.BF16, 93)
+    drop = (1234, 7, p)
+    E = L.ENGINE_TCGEN05
+    out0 = torch.empty((Bsz * N, D), dtype=torch.bfloat16, device=DEV)
+    out1 = torch.empty_like(out0)
+    lse0 = torch.empty((Bsz, H, N), device=DEV)
+    lse1 = torch.empty_like(lse0)
+    kb = ops.attn_keepbits(E, Bsz, N, H, drop, torch.device(DEV))
+    assert kb is not None and kb.numel() == Bsz * H * ((N + 127) // 128) ** 2 * 128 * 8 * 4
+    kb.fill_(0xA5)  # stale garbage must not leak into valid elements
+    ops.attn_fwd(E, L.BF16, qkv, out0, lse0, Bsz, N, H, hd, drop)
+    ops.attn_fwd(E, L.BF16, qkv, out1, lse1, Bsz, N, H, hd, drop, keepbits=kb)
+    assert torch.equal(out0, out1) and torch.equal(lse0, lse1)
+    d0 = torch.full_like(qkv, float("nan"))
+    d1 = torch.full_like(qkv, float("nan"))
+    ops.attn_bwd(E, L.BF16, qkv, out0, dout, lse0, d0, Bsz, N, H, hd, drop)
+    ops.attn_bwd(E, L.BF16, qkv, out0, dout, lse0, d1, Bsz, N, H, hd, drop, keepbits=kb)
+    assert torch.isfinite(d1.float()).all()
+    # dK / dV are reduced inside one CTA in a fixed order: bit-identical.  dQ is accumulated with fp32 atomics across
+    # the key-tile CTAs, whose order differs from launch to launch: equal to rounding.
+    assert torch.equal(d0[:, D:], d1[:, D:])
+    assert rel_err(d1[:, :D].float(), d0[:, :D].float()) < 1e-3
+    # the keep rate recorded in the cache (valid query rows / keys only) is 1 - p
+    nt = (N + 127) // 128
+    words = kb.view(torch.int32).view(Bsz * H, nt, nt, 128, 8)
+    bits = torch.stack([(words >> s) & 1 for s in list(range(8)) + list(range(16, 24))], dim=-1)  # [..., 8 grp, 16]
+    # element 2t -> bit t, element 2t+1 -> bit 16+t: reorder to key order
+    order = [i // 2 + (8 if i % 2 else 0) for i in range(16)]
+    bits = bits[..., order].reshape(Bsz * H, nt, nt, 128, 128)
+    full = bits.permute(0, 1, 3, 2, 4).reshape(Bsz * H, nt * 128, nt * 128)[:, :N, :N].float()
+    assert abs(full.mean().item() - (1 - p)) < 4.0 * (p * (1 - p) / full.numel()) ** 0.5 + 1e-3
+    # ... and it is the oracle's mask (numpy restatement of the generator)
+    from oracle import dropout_ref
+    Np = (N + 15) // 16 * 16
+    ref0 = dropout_ref.keep_mask(drop[0], drop[1], p, 0, N * Np).reshape(N, Np)[:, :N]  # (b, h) = (0, 0): q * Np + k
+    assert (torch.from_numpy(ref0.astype("float32")) == full[0].cpu()).all()
+
+
 @pytest.mark.parametrize("engine,dtype,tag", ATTN_ENGINES, ids=[e[2] for e in ATTN_ENGINES])
 def test_attention_dropout_consistency(engine, dtype, tag):
     """With dropout the mask cannot match torch's Philox stream; check keep-rate, 1/(1-p) scaling and

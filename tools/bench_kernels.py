@@ -123,6 +123,16 @@ def main():
             csq = torch.zeros(3 * D, device=DEV)
             ms = timeit(lambda: ops.attn_bwd(E, T, qkv, out, dout, lse, dqkv, B, N, H, hd, d, colsum=csq), a.reps)
             report(f"attn bwd {tag} + fused qkv-bias colsum", ms, 2 * fl)
+            if d:
+                kb = ops.attn_keepbits(E, B, N, H, d, qkv.device)
+                ms = timeit(lambda: ops.attn_fwd(E, T, qkv, out, lse, B, N, H, hd, d, keepbits=kb), a.reps)
+                report(f"attn fwd {tag} + keep-bit cache written", ms, fl)
+                ms = timeit(lambda: ops.attn_bwd(E, T, qkv, out, dout, lse, dqkv, B, N, H, hd, d, keepbits=kb), a.reps)
+                report(f"attn bwd {tag}, masks from the keep-bit cache", ms, 2 * fl)
+                ms = timeit(lambda: ops.attn_bwd(E, T, qkv, out, dout, lse, dqkv, B, N, H, hd, d, colsum=csq, keepbits=kb),
+                            a.reps)
+                report(f"attn bwd {tag}, keep-bit cache + fused colsum", ms, 2 * fl)
+                del kb
             # again in the opposite order: under the power cap the clocks sag over a long run of launches, which would
             # otherwise always be charged to whichever variant is timed last
             ms = timeit(lambda: ops.attn_bwd(E, T, qkv, out, dout, lse, dqkv, B, N, H, hd, d), a.reps)
