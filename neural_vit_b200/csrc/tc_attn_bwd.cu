@@ -292,7 +292,8 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   // buffered TMEM operand that must be free again before the next tile's first half is written.  With dropout the
   // softmax halves are long enough to hide that (7.9 -> 7.7 ms per launch); without dropout they are not (6.0 ->
   // 6.6 ms), so the variant is tied to the dropout instantiation.
-  constexpr bool kTsDq = ((kDrop && TVIT_ATTN_BWD_TSDQ) || kFull) && !kT;
+  // With the keep-flag cache (kBits) the softmax halves are short again and the smem operand wins (6.5 vs 7.0 ms).
+  constexpr bool kTsDq = ((kDrop && !kBits && TVIT_ATTN_BWD_TSDQ) || kFull) && !kT;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;

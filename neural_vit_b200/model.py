@@ -245,6 +245,7 @@ class _EmbedFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 # TVIT_ATTN_KEEPBITS=0 makes the backward kernel regenerate the attention dropout masks (A-B timing; same results)
 _USE_KEEPBITS = os.environ.get("TVIT_ATTN_KEEPBITS", "1") != "0"
+_FUSE_ATTN_CS = os.environ.get("TVIT_ATTN_FUSE_CS", "1") != "0"  # A-B timing of the fused qkv-bias column sums
 
 
 def _block_forward(h, n1w, n1b, qkvw, qkvb, pw, pb, g1, n2w, n2b, f1w, f1b, f2w, f2b, g2, s1, s2,
@@ -395,7 +396,7 @@ class _BlockFn(torch.autograd.Function):
         d_qkvb, _ = _dst(sk, I_QKVB, (3 * D,), dev)
         # colsum(dqkv) (the qkv-bias gradient) is folded into the attention-backward kernels when that is a net win:
         # with dropout the issue-bound kernel hides it (+0.13 ms vs 0.22 ms for a separate pass), without it does not
-        fuse_cs = d_attn is not None or rt.attn_engine != L.ENGINE_TCGEN05
+        fuse_cs = (d_attn is not None and _FUSE_ATTN_CS) or rt.attn_engine != L.ENGINE_TCGEN05
         ops.attn_bwd(rt.attn_engine, T, qkv, ao, dao, lse, dqkv, B, N, H, hd, d_attn, colsum=d_qkvb if fuse_cs else None,
                      keepbits=keepbits)
         if not fuse_cs:
