@@ -145,10 +145,11 @@ def ncu_traffic_bytes(name):
     if name != "c2":
         return None
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-    for fn in ("r2_ncu_attn_B256_dropout.json", "r1_ncu_attn_final_B256_dropout.json"):
+    for fn in ("r2b_ncu_attn_keepbits_B256_dropout.json", "r2_ncu_attn_B256_dropout.json",
+               "r1_ncu_attn_final_B256_dropout.json"):
         try:
             with open(os.path.join(ROOT, "profiles", fn)) as fh:
-                k = next(e for e in json.load(fh) if "tc_attn_bwd_kernel<1>" in e["kernel"])
+                k = next(e for e in json.load(fh) if "tc_attn_bwd_kernel" in e["kernel"])
             total = 0.0
             for m in ("dram_rd", "dram_wr"):
                 v, u = k[m].split()
