@@ -126,9 +126,9 @@ int tvit_gemm(const tvit_gemm_args* args, tvit_stream_t stream);
  * Dropout on the probabilities: element index = ((b*H + h)*N + q)*Np + k, Np = N rounded up to 16.
  * Replaces model.py:108-115 (reshape/permute, q@k^T*scale, softmax, attn_drop, @v, transpose).
  * ------------------------------------------------------------------------------------------- */
-/* keepbits (optional, tcgen05 engine with dropout only; NULL = off): a cache of the dropout site's keep flags, one
- * 32-bit word per 16-key group -- tvit_attn_keepbits_bytes() bytes, layout [(b,h)][q tile][key tile][128 rows][8 groups],
- * bit t / 16+t of a word = keep flag of key 2t / 2t+1 of the group.  tvit_attn_fwd writes it, tvit_attn_bwd of the same
+/* keepbits (optional, tcgen05 engine with dropout only; NULL = off): a cache of the dropout site's keep flags, one bit
+ * per element -- tvit_attn_keepbits_bytes() bytes, layout [(b,h)][q tile][key tile][128 rows][8 groups] of 16-bit fields,
+ * bit t / 8+t of a field = keep flag of key 2t / 2t+1 of the 16-key group.  tvit_attn_fwd writes it, tvit_attn_bwd of the same
  * (qkv, drop) reads it instead of running the generator again: same masks, ~8 % fewer instructions in the backward
  * kernel.  The cache is a pure function of (drop, shape); passing NULL to either call changes no result. */
 size_t tvit_attn_keepbits_bytes(int engine, int B, int N, int H); /* 0 for engines that do not use the cache */

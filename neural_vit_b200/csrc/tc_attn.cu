@@ -191,9 +191,9 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
       m2 = tail_score() * scale_log2;
       if (hf == 0) l = 1.0f;  // ex2(0); the partners' row sums are added at the end: only one of them counts the tail
     }
-    // keep-bit records of this CTA's query tile: [(b,h)][q tile][key tile][row][8 groups] 32-bit words
+    // keep-bit records of this CTA's query tile: [(b,h)][q tile][key tile][row][8 groups] 16-bit fields
     const int nkt_all = (N + kTile - 1) / kTile;
-    uint32_t* kb_tile = keepbits + ((((long long)b * H + h) * gridDim.x + blockIdx.x) * nkt_all * kTile + r) * 8 + hf * 4;
+    uint32_t* kb_tile = keepbits + ((((long long)b * H + h) * gridDim.x + blockIdx.x) * nkt_all * kTile + r) * 4 + hf * 2;
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&sm->s_full, (uint32_t)j & 1u);
       tc_fence_after();
@@ -299,8 +299,9 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
       up2(rs23, rs2, rs3);
       l = l * corr + ((rs0 + rs1) + (rs2 + rs3));
       m2 = m_new;
-      if (kDrop && keepbits)  // record (q tile, key tile j): [row r][8 groups] words; this thread owns groups hf*4 .. +3
-        st_global_v4(kb_tile + (long long)j * (kTile * 8), kbw[0], kbw[1], kbw[2], kbw[3]);
+      if (kDrop && keepbits)  // record (q tile, key tile j): [row r][8 groups] 16-bit fields; this thread owns groups
+        st_global_v2(kb_tile + (long long)j * (kTile * 4),  // hf*4 .. +3: bytes 0 / 2 of each kbw = even / odd keys
+                     prmt<0x6420u>(kbw[0], kbw[1]), prmt<0x6420u>(kbw[2], kbw[3]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -317,7 +318,7 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
         const bool keep_t = drop_keep(drop, rowe + (unsigned long long)Nk);
         if (!keep_t) pt = 0.f;
         // the tail key is element 0 of group 0 of key tile nkv (the backward CTA of that key tile reads it there)
-        if (keepbits && hf == 0) kb_tile[(long long)nkv * (kTile * 8)] = keep_t ? 1u : 0u;
+        if (keepbits && hf == 0) kb_tile[(long long)nkv * (kTile * 4)] = keep_t ? 1u : 0u;
       }
     }
     mbar_wait(&sm->pv_done, (uint32_t)(nkv - 1) & 1u);
@@ -371,10 +372,10 @@ static int make_qkv_tmap(CUtensorMap* tm, const void* qkv, int B, int N, int D3,
   return make_tmap_bf16(tm, qkv, 3, dims, strides, box);
 }
 
-// keep-bit cache of the attention-probability dropout site (include/tvit.h): one 32-bit word per 16-key group
+// keep-bit cache of the attention-probability dropout site (include/tvit.h): 16 bits per 16-key group
 size_t tc_attn_keepbits_bytes(int B, int N, int H) {
   const size_t nt = (size_t)((N + kTile - 1) / kTile);
-  return (size_t)B * H * nt * nt * kTile * 8 * sizeof(uint32_t);
+  return (size_t)B * H * nt * nt * kTile * 8 * sizeof(uint16_t);
 }
 
 int tc_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, const tvit_dropout* drop,

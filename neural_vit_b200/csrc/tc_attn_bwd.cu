@@ -717,13 +717,16 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     // 32-bit row term (q * npad / 16 < 2^32 for every N this kernel accepts)
     const uint32_t npad16 = (uint32_t)((N + 15) >> 4);
     const unsigned long long grp_cta = (attn_drop_row_base(b, H, h, N, 0) + (unsigned long long)kv0) >> 4;
-    // keep-bit records of this key tile: [(b,h)][q tile][key tile][row][8 groups]; this thread reads groups chunk, 4 + chunk
-    const uint32_t* kb_row = kBits ? keepbits + ((((long long)b * H + h) * nqt * nqt + jt) * kTileB + r) * 8 + chunk : nullptr;
-    const int kb_qstride = nqt * kTileB * 8;
+    // keep-bit records of this key tile: [(b,h)][q tile][key tile][row][8 groups] 16-bit fields (bits 0-7: even keys,
+    // 8-15: odd keys); this thread reads groups chunk and 4 + chunk = half (chunk & 1) of words chunk >> 1 and 2 + (chunk >> 1)
+    const uint32_t* kb_row =
+        kBits ? keepbits + ((((long long)b * H + h) * nqt * nqt + jt) * kTileB + r) * 4 + (chunk >> 1) : nullptr;
+    const int kb_qstride = nqt * kTileB * 4;
+    const uint32_t kb_sel = (chunk & 1) ? 0x4342u : 0x4140u;  // prmt: field -> [even byte, 0, odd byte, 0]
     uint32_t kb_next0 = 0, kb_next1 = 0;
     if (kBits) {
       kb_next0 = __ldg(kb_row + qt * kb_qstride);
-      kb_next1 = __ldg(kb_row + qt * kb_qstride + 4);
+      kb_next1 = __ldg(kb_row + qt * kb_qstride + 2);
     }
     for (int i = 0; i < nq; ++i) {
       const float nlse2 = nl_next, negDq = nd_next;
@@ -736,7 +739,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         nd_next = stat_row[qt * 256 + 128];
         if (kBits) {
           kb_next0 = __ldg(kb_row + qt * kb_qstride);
-          kb_next1 = __ldg(kb_row + qt * kb_qstride + 4);
+          kb_next1 = __ldg(kb_row + qt * kb_qstride + 2);
         }
       }
       const uint32_t aDSbuf = smem_u32(sDS) + (uint32_t)(i & 1) * kPBytes;
@@ -755,7 +758,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (lane == 0) mbar_arrive(&sm->s_free[hf]);  // this half's S / dP columns may be refilled
         uint32_t pk[8], dk[8];
         uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0;
-        const uint32_t kbw = hf == 0 ? kb0 : kb1;  // kBits: bit t / 16 + t = keep flag of element 2t / 2t + 1
+        const uint32_t kbw = kBits ? prmt_r(hf == 0 ? kb0 : kb1, 0u, kb_sel) : 0u;  // bit t / 16 + t: element 2t / 2t + 1
         if (kDrop && !kBits) {  // this thread's 16 keys are exactly one Philox group (common.cuh)
           const unsigned long long grp = grp_row + (unsigned long long)(hf * 4 + chunk);
           drop_bits16(drop, grp, w);

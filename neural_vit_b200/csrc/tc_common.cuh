@@ -41,6 +41,10 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+__device__ __forceinline__ void st_global_v2(void* p, uint32_t a, uint32_t b) {
+  asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -372,7 +372,7 @@ def test_attention_keepbits_cache_reproduces_the_generated_masks(Bsz, N, H, p):
     lse0 = torch.empty((Bsz, H, N), device=DEV)
     lse1 = torch.empty_like(lse0)
     kb = ops.attn_keepbits(E, Bsz, N, H, drop, torch.device(DEV))
-    assert kb is not None and kb.numel() == Bsz * H * ((N + 127) // 128) ** 2 * 128 * 8 * 4
+    assert kb is not None and kb.numel() == Bsz * H * ((N + 127) // 128) ** 2 * 128 * 8 * 2
     kb.fill_(0xA5)  # stale garbage must not leak into valid elements
     ops.attn_fwd(E, L.BF16, qkv, out0, lse0, Bsz, N, H, hd, drop)
     ops.attn_fwd(E, L.BF16, qkv, out1, lse1, Bsz, N, H, hd, drop, keepbits=kb)
@@ -388,9 +388,9 @@ def test_attention_keepbits_cache_reproduces_the_generated_masks(Bsz, N, H, p):
     assert rel_err(d1[:, :D].float(), d0[:, :D].float()) < 1e-3
     # the keep rate recorded in the cache (valid query rows / keys only) is 1 - p
     nt = (N + 127) // 128
-    words = kb.view(torch.int32).view(Bsz * H, nt, nt, 128, 8)
-    bits = torch.stack([(words >> s) & 1 for s in list(range(8)) + list(range(16, 24))], dim=-1)  # [..., 8 grp, 16]
-    # element 2t -> bit t, element 2t+1 -> bit 16+t: reorder to key order
+    words = kb.view(torch.int16).view(Bsz * H, nt, nt, 128, 8).to(torch.int32)
+    bits = torch.stack([(words >> s) & 1 for s in range(16)], dim=-1)  # [..., 8 groups, 16 bits]
+    # element 2t -> bit t, element 2t+1 -> bit 8+t: reorder to key order
     order = [i // 2 + (8 if i % 2 else 0) for i in range(16)]
     bits = bits[..., order].reshape(Bsz * H, nt, nt, 128, 128)
     full = bits.permute(0, 1, 3, 2, 4).reshape(Bsz * H, nt * 128, nt * 128)[:, :N, :N].float()
