@@ -39,6 +39,9 @@ namespace tvit {
 #ifndef TVIT_ATTN_BWD_TSDQ
 #define TVIT_ATTN_BWD_TSDQ 1  // 0: dQ reads dS from shared memory in the dropout instantiation too (A-B builds)
 #endif
+#ifndef TVIT_ATTN_BWD_TSDQ_BITS
+#define TVIT_ATTN_BWD_TSDQ_BITS 0  // 1: the keep-flag-cache instantiation takes dS for dQ from TMEM as well (A-B builds)
+#endif
 #ifndef TVIT_ATTN_BWD_T_DEFAULT
 #define TVIT_ATTN_BWD_T_DEFAULT 0
 #endif
@@ -293,7 +296,7 @@ tc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   // softmax halves are long enough to hide that (7.9 -> 7.7 ms per launch); without dropout they are not (6.0 ->
   // 6.6 ms), so the variant is tied to the dropout instantiation.
   // With the keep-flag cache (kBits) the softmax halves are short again and the smem operand wins (6.5 vs 7.0 ms).
-  constexpr bool kTsDq = ((kDrop && !kBits && TVIT_ATTN_BWD_TSDQ) || kFull) && !kT;
+  constexpr bool kTsDq = ((kDrop && (!kBits || TVIT_ATTN_BWD_TSDQ_BITS) && TVIT_ATTN_BWD_TSDQ) || kFull) && !kT;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
