@@ -12,7 +12,9 @@
 // address function), so neither P nor dS is ever transposed.  dQ_i partial tiles are drained by four
 // dedicated warps with coalesced 16-byte fp32 reductions into a tile-chunked accumulator and converted
 // to bf16 by a finishing kernel; dK_j / dV_j stay in TMEM across the whole query loop.
-// D = rowsum(dO o O) and lse are read per query row (one scalar each per thread per tile).
+// D = rowsum(dO o O) and lse reach the softmax threads as ready-made per-query records [-lse2 | -D'] written by the
+// prep kernel (one pair of scalars per thread and tile, loaded one tile ahead).  With dropout the keep flags are either
+// regenerated (Philox, one call per 16 keys) or -- kBits -- read from the cache the forward kernel wrote.
 //
 // Pipelining.  TMEM (512 columns: S 128, dP 128, dV 64, dK 64, dQ 64) has no room for a second S / dP tile, so
 // the tile is pipelined by key halves instead: S and dP are issued as two N = 64 MMA groups (keys [0,64) and

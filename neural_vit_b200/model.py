@@ -395,7 +395,8 @@ class _BlockFn(torch.autograd.Function):
         dqkv = _empty((M, 3 * D), td, dev)
         d_qkvb, _ = _dst(sk, I_QKVB, (3 * D,), dev)
         # colsum(dqkv) (the qkv-bias gradient) is folded into the attention-backward kernels when that is a net win:
-        # with dropout the issue-bound kernel hides it (+0.13 ms vs 0.22 ms for a separate pass), without it does not
+        # with dropout it is (whole C2 step 1510-1516 vs 1501-1502 samples/s with the separate 0.2 ms pass,
+        # alternating runs on one box), without dropout it is not
         fuse_cs = (d_attn is not None and _FUSE_ATTN_CS) or rt.attn_engine != L.ENGINE_TCGEN05
         ops.attn_bwd(rt.attn_engine, T, qkv, ao, dao, lse, dqkv, B, N, H, hd, d_attn, colsum=d_qkvb if fuse_cs else None,
                      keepbits=keepbits)
