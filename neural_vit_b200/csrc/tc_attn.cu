@@ -15,6 +15,10 @@
 // {3D, N, B} (rows past N are zero-filled by TMA), the output is written token-major [B*N, H*64].
 #include "tc_common.cuh"
 
+#ifndef TVIT_ATTN_FWD_PASSW
+#define TVIT_ATTN_FWD_PASSW 16
+#endif
+
 namespace tvit {
 
 constexpr int kHd = 64;
@@ -246,28 +250,33 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
       uint32_t kbw[4] = {0, 0, 0, 0};  // keep bits of this thread's four 16-key groups of the tile
       const f32x2 sl2 = pk2(scale_log2, scale_log2), nm2 = pk2(-m_new, -m_new);
       const unsigned long long g0 = (rowe + (unsigned long long)j * kTile + hf * 64) >> 4;  // 16-element groups
+      // kPassW scores per TMEM load: 32 without dropout; 16 with it, where the Philox state, the masks and the keep-bit
+      // words compete for the 96 registers that two CTAs per SM allow (TVIT_ATTN_FWD_PASSW: A-B builds)
+      constexpr int kPassW = kDrop ? TVIT_ATTN_FWD_PASSW : 32;
 #pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
-        uint32_t sv[32];
-        tmem_ld32(tS + lane_off + hf * 64 + c2 * 32, sv);
+      for (int cw = 0; cw < 64 / kPassW; ++cw) {
+        uint32_t sv[kPassW];
+        if constexpr (kPassW == 32) tmem_ld32(tS + lane_off + hf * 64 + cw * 32, sv);
+        else tmem_ld16(tS + lane_off + hf * 64 + cw * 16, sv);
         tmem_ld_wait();
-        if (c2 == 1) {  // both halves of S are now in registers / consumed: release the S buffer
+        if (cw == 64 / kPassW - 1) {  // all of S is now in registers / consumed: release the S buffer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm->s_free);
         }
         if (valid < 64) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c2 * 32 + c >= valid) sv[c] = 0xff800000u;  // -inf
+          for (int c = 0; c < kPassW; ++c)
+            if (cw * kPassW + c >= valid) sv[c] = 0xff800000u;  // -inf
         }
-        uint32_t pk[16];
+        uint32_t pk[kPassW / 2];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {  // one Philox call per 16 keys (common.cuh: attention-probability dropout)
+        for (int g = 0; g < kPassW / 16; ++g) {  // one Philox call per 16 keys (common.cuh: attention-probability dropout)
+          const int gi = cw * (kPassW / 16) + g;  // 16-key group of this thread's 64 keys
           uint32_t w[4] = {0, 0, 0, 0}, tg2 = 0, kb = 0;
           if (kDrop) {
-            drop_bits16(drop, g0 + c2 * 2 + g, w);
-            tg2 = drop_tgc(drop_thr8(drop, g0 + c2 * 2 + g));
+            drop_bits16(drop, g0 + gi, w);
+            tg2 = drop_tgc(drop_thr8(drop, g0 + gi));
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -290,9 +299,10 @@ tc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat
             pk[g * 8 + u * 2] = v01;
             pk[g * 8 + u * 2 + 1] = v23;
           }
-          if (kDrop) kbw[c2 * 2 + g] = kb;
+          if (kDrop) kbw[gi] = kb;
         }
-        tmem_st16(tP + lane_off + hf * 32 + c2 * 16, pk);
+        if constexpr (kPassW == 32) tmem_st16(tP + lane_off + hf * 32 + cw * 16, pk);
+        else tmem_st8(tP + lane_off + hf * 32 + cw * 8, pk);
       }
       float rs0, rs1, rs2, rs3;
       up2(rs01, rs0, rs1);
