@@ -1,0 +1,6 @@
+// explicit instantiation of the tcgen05 GEMM for BN = 192 (tc_gemm_impl.cuh)
+#include "tc_gemm_impl.cuh"
+
+namespace tvit {
+template int dispatch_epi<192>(const tvit_gemm_args*, const GemmShape&, const EpiParams&, cudaStream_t);
+}  // namespace tvit
