@@ -373,10 +373,15 @@ def test_attention_keepbits_cache_reproduces_the_generated_masks(Bsz, N, H, p):
     lse1 = torch.empty_like(lse0)
     kb = ops.attn_keepbits(E, Bsz, N, H, drop, torch.device(DEV))
     assert kb is not None and kb.numel() == Bsz * H * ((N + 127) // 128) ** 2 * 128 * 8 * 2
-    kb.fill_(0xA5)  # stale garbage must not leak into valid elements
+    # the cache sits between two guard regions that the forward kernel must leave untouched; stale garbage inside
+    # it must not leak into valid elements
+    guard = 4096
+    arena = torch.full((kb.numel() + 2 * guard,), 0xA5, dtype=torch.uint8, device=DEV)
+    kb = arena[guard:guard + kb.numel()]
     ops.attn_fwd(E, L.BF16, qkv, out0, lse0, Bsz, N, H, hd, drop)
     ops.attn_fwd(E, L.BF16, qkv, out1, lse1, Bsz, N, H, hd, drop, keepbits=kb)
     assert torch.equal(out0, out1) and torch.equal(lse0, lse1)
+    assert (arena[:guard] == 0xA5).all() and (arena[guard + kb.numel():] == 0xA5).all()
     d0 = torch.full_like(qkv, float("nan"))
     d1 = torch.full_like(qkv, float("nan"))
     ops.attn_bwd(E, L.BF16, qkv, out0, dout, lse0, d0, Bsz, N, H, hd, drop)
