@@ -98,7 +98,7 @@ typedef struct {
   void* out;
   long long ldo;
   const float* bias; /* [N] or NULL */
-  void* aux;         /* BIAS_GELU: d out / d pre-activation (out); GELU_BWD: the same tensor (in) */
+  void* aux;         /* BIAS_GELU: d out / d pre-activation (out; NULL = not wanted: inference); GELU_BWD: the same (in) */
   long long ldaux;
   const float* resid; /* RESIDUAL */
   long long ldres;

@@ -74,8 +74,7 @@ extern "C" int tvit_gemm(const tvit_gemm_args* a, tvit_stream_t stream) {
   TVIT_CHECK_ARG(a->M >= 0 && a->N > 0 && a->K > 0, "gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   if (a->M == 0) return TVIT_OK;
   switch (a->epilogue) {
-    case TVIT_EPI_BIAS_GELU:
-    case TVIT_EPI_GELU_BWD:
+    case TVIT_EPI_GELU_BWD:  // (BIAS_GELU: aux is optional -- an inference forward has no use for it)
       TVIT_CHECK_ARG(a->aux != nullptr, "gemm: epilogue %d needs aux", a->epilogue);
       break;
     case TVIT_EPI_RESIDUAL:

@@ -101,7 +101,7 @@ __device__ __forceinline__ void epi_apply1(const EpiParams& p, int m, int n, flo
   } else if (EPI == TVIT_EPI_BIAS_GELU) {
     if (p.bias) v += p.bias[n];
     const float mlt = drop_mult(p.drop, (unsigned long long)m * p.N + n);
-    Act<T>::st((T*)p.aux + m * p.ldaux + n, gelu_grad_t<T>(v) * mlt);
+    if (p.aux) Act<T>::st((T*)p.aux + m * p.ldaux + n, gelu_grad_t<T>(v) * mlt);
     Act<T>::st((T*)p.out + m * p.ldo + n, gelu_t<T>(v) * mlt);
   } else if (EPI == TVIT_EPI_RESIDUAL) {
     if (p.bias) v += p.bias[n];
@@ -152,9 +152,10 @@ __device__ __forceinline__ void epi_apply4(const EpiParams& p, int m, int n0, fl
     }
     float mlt[4];
     drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, mlt);
-    st4((T*)p.aux + m * p.ldaux + n0,
-        make_float4(gelu_grad_t<T>(v.x) * mlt[0], gelu_grad_t<T>(v.y) * mlt[1], gelu_grad_t<T>(v.z) * mlt[2],
-                    gelu_grad_t<T>(v.w) * mlt[3]));
+    if (p.aux)
+      st4((T*)p.aux + m * p.ldaux + n0,
+          make_float4(gelu_grad_t<T>(v.x) * mlt[0], gelu_grad_t<T>(v.y) * mlt[1], gelu_grad_t<T>(v.z) * mlt[2],
+                      gelu_grad_t<T>(v.w) * mlt[3]));
     st4((T*)p.out + m * p.ldo + n0,
         make_float4(gelu_t<T>(v.x) * mlt[0], gelu_t<T>(v.y) * mlt[1], gelu_t<T>(v.z) * mlt[2], gelu_t<T>(v.w) * mlt[3]));
   } else if (EPI == TVIT_EPI_RESIDUAL) {
@@ -232,7 +233,7 @@ __device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, co
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] = gelu_grad_t<T>(x[j]) * ml[j];
       uint4 h = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
-      *reinterpret_cast<uint4*>((__nv_bfloat16*)p.aux + m * p.ldaux + n0) = h;
+      if (p.aux) *reinterpret_cast<uint4*>((__nv_bfloat16*)p.aux + m * p.ldaux + n0) = h;
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = gelu_t<T>(x[j]) * ml[j];
     } else {  // GELU_BWD
@@ -394,7 +395,7 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
         dv[j] &= mk[j];
       }
     }
-    st_global_v8((__nv_bfloat16*)p.aux + m * p.ldaux + nc, dv);
+    if (p.aux) st_global_v8((__nv_bfloat16*)p.aux + m * p.ldaux + nc, dv);  // NULL in an inference forward
     st_global_v8((__nv_bfloat16*)p.out + m * p.ldo + nc, v);
     return;
   }

@@ -84,6 +84,18 @@ def test_gemm_bias_gelu(engine, dtype, tag):
     assert torch.equal(out_d.float()[~keep], torch.zeros_like(out_d.float()[~keep]))
     assert rel_err(out_d.float()[keep], out.float()[keep] / 0.75) < 2 * _tol(dtype) + 1e-3
     assert rel_err(aux_d.float()[keep], aux.float()[keep] / 0.75) < 2 * _tol(dtype) + 1e-3
+    # an inference forward passes no aux buffer: the same `out` bits, nothing else written
+    out_n = torch.empty_like(out)
+    ops.gemm(engine, dtype, a, b, M, N, K, epilogue=L.EPI_BIAS_GELU, out=out_n, bias=bias)
+    assert torch.equal(out_n, out)
+    # ... also on the weight-stationary tcgen05 path (enough m-tiles for every SM) and with a ragged last m-tile
+    if engine == L.ENGINE_TCGEN05:
+        M2 = 128 * 2 * 148 + 77
+        a2 = _rand((M2, K), dtype, 60)
+        o1, o2, x1 = (torch.empty((M2, N), dtype=td, device=DEV) for _ in range(3))
+        ops.gemm(engine, dtype, a2, b, M2, N, K, epilogue=L.EPI_BIAS_GELU, out=o1, aux=x1, bias=bias)
+        ops.gemm(engine, dtype, a2, b, M2, N, K, epilogue=L.EPI_BIAS_GELU, out=o2, bias=bias)
+        assert torch.equal(o1, o2)
 
 
 @pytest.mark.parametrize("engine,dtype,tag", ENGINES, ids=[e[2] for e in ENGINES])
