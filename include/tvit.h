@@ -98,7 +98,8 @@ typedef struct {
   void* out;
   long long ldo;
   const float* bias; /* [N] or NULL */
-  void* aux;         /* BIAS_GELU: d out / d pre-activation (out; NULL = not wanted: inference); GELU_BWD: the same (in) */
+  void* aux;         /* BIAS_GELU: d out / d pre-activation (out; NULL = not wanted: an inference forward -- the tcgen05
+                        engine then takes no dropout); GELU_BWD: the same tensor (in) */
   long long ldaux;
   const float* resid; /* RESIDUAL */
   long long ldres;

@@ -5,6 +5,12 @@
 
 namespace tvit {
 
+// Internal epilogue id: BIAS_GELU without the aux output (tvit_gemm_args.aux == NULL, an inference forward).  A template
+// instantiation of its own on the tcgen05 path, so that the training kernel keeps its unconditional aux store (a
+// predicated store in the shared kernel cost the training fc1 GEMM 2.5 %).
+constexpr int kEpiBiasGeluNoAux = 101;
+__host__ __device__ constexpr bool is_bias_gelu(int epi) { return epi == TVIT_EPI_BIAS_GELU || epi == kEpiBiasGeluNoAux; }
+
 struct EpiParams {
   int M, N;
   void* out;
@@ -98,10 +104,10 @@ __device__ __forceinline__ void epi_apply1(const EpiParams& p, int m, int n, flo
   if (EPI == TVIT_EPI_STORE) {
     if (p.bias) v += p.bias[n];
     Act<T>::st((T*)p.out + m * p.ldo + n, v);
-  } else if (EPI == TVIT_EPI_BIAS_GELU) {
+  } else if (is_bias_gelu(EPI)) {
     if (p.bias) v += p.bias[n];
     const float mlt = drop_mult(p.drop, (unsigned long long)m * p.N + n);
-    if (p.aux) Act<T>::st((T*)p.aux + m * p.ldaux + n, gelu_grad_t<T>(v) * mlt);
+    if (EPI == TVIT_EPI_BIAS_GELU) Act<T>::st((T*)p.aux + m * p.ldaux + n, gelu_grad_t<T>(v) * mlt);
     Act<T>::st((T*)p.out + m * p.ldo + n, gelu_t<T>(v) * mlt);
   } else if (EPI == TVIT_EPI_RESIDUAL) {
     if (p.bias) v += p.bias[n];
@@ -145,14 +151,14 @@ __device__ __forceinline__ void epi_apply4(const EpiParams& p, int m, int n0, fl
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
     st4((T*)p.out + m * p.ldo + n0, v);
-  } else if (EPI == TVIT_EPI_BIAS_GELU) {
+  } else if (is_bias_gelu(EPI)) {
     if (p.bias) {
       const float4 b = ld4(p.bias + n0);
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
     float mlt[4];
     drop_mult4e(p.drop, (unsigned long long)m * p.N + n0, mlt);
-    if (p.aux)
+    if (EPI == TVIT_EPI_BIAS_GELU)
       st4((T*)p.aux + m * p.ldaux + n0,
           make_float4(gelu_grad_t<T>(v.x) * mlt[0], gelu_grad_t<T>(v.y) * mlt[1], gelu_grad_t<T>(v.z) * mlt[2],
                       gelu_grad_t<T>(v.w) * mlt[3]));
@@ -211,7 +217,7 @@ __device__ __forceinline__ void epi_apply4(const EpiParams& p, int m, int n0, fl
 template <int EPI, typename T>
 __device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, const float (&v)[8]) {
   constexpr bool kWide = (sizeof(T) == 2) &&
-                         (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_GELU_BWD);
+                         (EPI == TVIT_EPI_STORE || is_bias_gelu(EPI) || EPI == TVIT_EPI_GELU_BWD);
   if (kWide && p.vec8_ok && n0 + 8 <= p.N && !(EPI == TVIT_EPI_GELU_BWD && p.colsum)) {
     float x[8];
 #pragma unroll
@@ -226,14 +232,14 @@ __device__ __forceinline__ void epi_apply8(const EpiParams& p, int m, int n0, co
       *reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + m * p.ldo + n0) = o;
       return;
     }
-    if (EPI == TVIT_EPI_BIAS_GELU) {
+    if (is_bias_gelu(EPI)) {
       float ml[8];
       drop_mult8(p.drop, (unsigned long long)m * p.N + n0, ml);  // vec8_ok: N % 8 == 0 and n0 % 8 == 0
       float d[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] = gelu_grad_t<T>(x[j]) * ml[j];
       uint4 h = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
-      if (p.aux) *reinterpret_cast<uint4*>((__nv_bfloat16*)p.aux + m * p.ldaux + n0) = h;
+      if (EPI == TVIT_EPI_BIAS_GELU) *reinterpret_cast<uint4*>((__nv_bfloat16*)p.aux + m * p.ldaux + n0) = h;
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = gelu_t<T>(x[j]) * ml[j];
     } else {  // GELU_BWD
@@ -321,7 +327,7 @@ template <int EPI, bool kDrop>
 __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, uint32_t s_gamma, float row_scale, int m,
                                          int nc, uint32_t taddr, bool row_ok, const uint32_t (&ext)[16],
                                          float (&colv)[16]) {
-  constexpr bool kBias = (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL);
+  constexpr bool kBias = (EPI == TVIT_EPI_STORE || is_bias_gelu(EPI) || EPI == TVIT_EPI_RESIDUAL);
   uint32_t acc[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -371,7 +377,8 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
     st_global_v8((__nv_bfloat16*)p.out + m * p.ldo + nc, v);
     return;
   }
-  if (EPI == TVIT_EPI_BIAS_GELU) {
+  if (is_bias_gelu(EPI)) {
+    constexpr bool kAux = EPI == TVIT_EPI_BIAS_GELU;  // kEpiBiasGeluNoAux: inference forward, `out` only
     // out = drop(gelu(h)),  aux = dropmask/(1-p) * gelu'(h): the factor the backward GEMM's epilogue multiplies by, so
     // GELU_BWD needs neither the activation derivative nor the mask generator.  bf16 outputs: the keep masks are
     // applied to packed bf16 pairs (one Philox call, then two prmt and an integer subtract per pair).
@@ -384,7 +391,7 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
       float x0, x1;
       up2(x[j], x0, x1);
       f32x2 y, d;
-      gelu_fast2<true, kDrop>(x0, x1, ks, y, d);
+      gelu_fast2<kAux, kDrop>(x0, x1, ks, y, d);
       float y0, y1, d0, d1;
       up2(y, y0, y1);
       up2(d, d0, d1);
@@ -395,7 +402,7 @@ __device__ __forceinline__ void tc_epi16(const EpiParams& p, uint32_t s_bias, ui
         dv[j] &= mk[j];
       }
     }
-    if (p.aux) st_global_v8((__nv_bfloat16*)p.aux + m * p.ldaux + nc, dv);  // NULL in an inference forward
+    if (kAux) st_global_v8((__nv_bfloat16*)p.aux + m * p.ldaux + nc, dv);
     st_global_v8((__nv_bfloat16*)p.out + m * p.ldo + nc, v);
     return;
   }

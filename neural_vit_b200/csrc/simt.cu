@@ -73,7 +73,8 @@ static int launch_simt_gemm(const tvit_gemm_args* a, cudaStream_t s) {
     simt_gemm_kernel<T, E><<<grid, 256, 0, s>>>((const T*)a->A, sam, sak, (const T*)a->B, sbn, sbk, a->M, \
                                                 a->N, a->K, ep);                                           \
     break;
-  switch (a->epilogue) {
+  switch (a->epilogue == TVIT_EPI_BIAS_GELU && !a->aux ? kEpiBiasGeluNoAux : a->epilogue) {
+    LAUNCH(kEpiBiasGeluNoAux)  // inference forward: no aux output (epilogue.cuh)
     LAUNCH(TVIT_EPI_STORE)
     LAUNCH(TVIT_EPI_BIAS_GELU)
     LAUNCH(TVIT_EPI_RESIDUAL)

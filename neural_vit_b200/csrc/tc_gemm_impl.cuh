@@ -292,7 +292,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      constexpr bool kFast = (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL ||
+      constexpr bool kFast = (EPI == TVIT_EPI_STORE || is_bias_gelu(EPI) || EPI == TVIT_EPI_RESIDUAL ||
                               EPI == TVIT_EPI_GELU_BWD);
       if (kFast && ep.vec16_ok) {
         const float rsc = (EPI == TVIT_EPI_RESIDUAL && ep.row_scale && row_ok) ? ep.row_scale[m / ep.rpg] : 1.0f;
@@ -399,7 +399,7 @@ static int launch_tc(const tvit_gemm_args* a, const GemmShape& sh, const EpiPara
   constexpr bool kCanDrop = (EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL || EPI == TVIT_EPI_PATCH_EMBED);
   // weight-stationary variant: K-major, K <= 384, BN = 192 divides N, enough m-tiles to keep every CTA busy
   constexpr bool kResOk = (BN == 192) && !MN &&
-                          (EPI == TVIT_EPI_STORE || EPI == TVIT_EPI_BIAS_GELU || EPI == TVIT_EPI_RESIDUAL ||
+                          (EPI == TVIT_EPI_STORE || is_bias_gelu(EPI) || EPI == TVIT_EPI_RESIDUAL ||
                            EPI == TVIT_EPI_GELU_BWD);
   if (kResOk && sh.k_blocks <= kMaxResKBlocks && sh.N % 192 == 0 && sh.m_tiles >= 2 * num_sms() &&
       getenv("TVIT_NO_BRES") == nullptr) {
@@ -420,7 +420,11 @@ int dispatch_epi(const tvit_gemm_args* a, const GemmShape& sh, const EpiParams& 
   }
   switch (a->epilogue) {
     case TVIT_EPI_STORE: return launch_tc<BN, false, TVIT_EPI_STORE>(a, sh, ep, s);
-    case TVIT_EPI_BIAS_GELU: return launch_tc<BN, false, TVIT_EPI_BIAS_GELU>(a, sh, ep, s);
+    case TVIT_EPI_BIAS_GELU:
+      if (a->aux) return launch_tc<BN, false, TVIT_EPI_BIAS_GELU>(a, sh, ep, s);
+      if (ep.drop.thr16 != 0)
+        return fail(TVIT_ERR_UNSUPPORTED, "tcgen05 gemm: BIAS_GELU without aux (inference) does not take dropout");
+      return launch_tc<BN, false, kEpiBiasGeluNoAux>(a, sh, ep, s);
     case TVIT_EPI_RESIDUAL: return launch_tc<BN, false, TVIT_EPI_RESIDUAL>(a, sh, ep, s);
     case TVIT_EPI_GELU_BWD: return launch_tc<BN, false, TVIT_EPI_GELU_BWD>(a, sh, ep, s);
     case TVIT_EPI_PATCH_EMBED: return launch_tc<BN, false, TVIT_EPI_PATCH_EMBED>(a, sh, ep, s);

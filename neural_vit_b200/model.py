@@ -288,7 +288,7 @@ def _block_forward(h, n1w, n1b, qkvw, qkvb, pw, pb, g1, n2w, n2b, f1w, f1b, f2w,
     mean2, rstd2 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
     ops.ln_fwd(h_mid, D, n2w, n2b, y2, T, mean2, rstd2, M, D)
     # d act / d pre-activation (GELU' x dropout multiplier), consumed by GELU_BWD; not produced when no backward follows
-    hpre = _empty((M, hid), td, dev) if need_grad else None
+    hpre = _empty((M, hid), td, dev) if (need_grad or d_fc1 is not None) else None
     act = _empty((M, hid), td, dev)
     ops.gemm(E, T, y2, fc1_w, M, hid, D, epilogue=L.EPI_BIAS_GELU, out=act, aux=hpre, bias=f1b, drop=d_fc1)
     h_out = torch.empty_like(h)
